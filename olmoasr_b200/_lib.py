@@ -1,0 +1,85 @@
+"""ctypes binding of liboasr_b200.so (the C ABI declared in include/oasr_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, an exception is
+raised.  Nothing in the product path computes on the CPU or through stock torch ops.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from pathlib import Path
+
+import torch
+
+_LIB_PATH = Path(__file__).resolve().parent / "csrc" / "liboasr_b200.so"
+_lib = None
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int
+c_i64 = ctypes.c_int64
+c_float = ctypes.c_float
+
+
+class OasrError(RuntimeError):
+    pass
+
+
+# name -> argtypes (restype is always int unless listed in _RESTYPES)
+_SIGNATURES = {
+    "oasr_abi_version": [],
+    "oasr_device_sm_count": [],
+    "oasr_gemm_bf16": [c_void_p, c_i64, c_int, c_void_p, c_i64, c_int, c_void_p, c_i64, c_void_p, c_void_p,
+                       c_void_p, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_void_p],
+}
+_RESTYPES = {"oasr_last_error": ctypes.c_char_p}
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def lib():
+    """Load (once) and return the ctypes handle.  Raises OasrError when the library is absent."""
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            raise OasrError(
+                f"{_LIB_PATH} not found: build it with `python -m olmoasr_b200.build` "
+                "(there is no CPU / eager fallback)"
+            )
+        h = ctypes.CDLL(str(_LIB_PATH), mode=ctypes.RTLD_GLOBAL)
+        h.oasr_last_error.restype = ctypes.c_char_p
+        h.oasr_last_error.argtypes = []
+        for name, args in _SIGNATURES.items():
+            fn = getattr(h, name)
+            fn.argtypes = args
+            fn.restype = _RESTYPES.get(name, c_int)
+        _lib = h
+    return _lib
+
+
+def exported_symbols():
+    """Names the header declares (used by the CPU-side ABI test)."""
+    return ["oasr_last_error", *_SIGNATURES.keys()]
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().oasr_last_error()
+        raise OasrError(f"{what or 'oasr call'} failed (rc={rc}): {msg.decode() if msg else ''}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name: str, *args):
+    fn = getattr(lib(), name)
+    check(fn(*args), name)

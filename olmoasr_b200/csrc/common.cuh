@@ -1,0 +1,83 @@
+// Shared host/device helpers for liboasr_b200. No torch types anywhere in csrc/.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/oasr_b200.h"
+
+namespace oasr {
+
+typedef __nv_bfloat16 bf16;
+
+#define OASR_CUDA_OK(expr)                                                                   \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      oasr::set_last_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return OASR_ERR_CUDA;                                                                  \
+    }                                                                                        \
+  } while (0)
+
+#define OASR_REQUIRE(cond, ...)              \
+  do {                                       \
+    if (!(cond)) {                           \
+      oasr::set_last_error(__VA_ARGS__);     \
+      return OASR_ERR_INVALID;               \
+    }                                        \
+  } while (0)
+
+#define OASR_LAUNCH_CHECK() OASR_CUDA_OK(cudaGetLastError())
+
+void set_last_error(const char* fmt, ...);
+int num_sms();
+
+// 2-D bf16/f32 row-major tensor map: `inner` contiguous elements per row, `outer` rows,
+// `row_stride_bytes` between rows, box = box_inner x box_outer, 128-byte swizzle when
+// swizzle128 (box_inner * elt must then be 128 bytes).
+int make_tmap_2d(CUtensorMap* out, const void* base, int elt_bytes, uint64_t inner, uint64_t outer,
+                 uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, bool swizzle128);
+int make_tmap_3d(CUtensorMap* out, const void* base, int elt_bytes, uint64_t d0, uint64_t d1,
+                 uint64_t d2, uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0,
+                 uint32_t b1, uint32_t b2, bool swizzle128);
+
+__host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- small device helpers ---------------------------------------------------------------
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  // nn.GELU() / F.gelu default: 0.5 x (1 + erf(x / sqrt(2)))   (reference olmoasr/model.py:480-482,592-593)
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(v);
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <typename T>
+__device__ __forceinline__ T warp_max(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+}  // namespace oasr

@@ -1,0 +1,401 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma
+// (single-thread issue, fp32 accumulators in TMEM, double-buffered) -> tcgen05.ld epilogue.
+//
+//   D[M,N] = epi( sum_k A[m,k] B[n,k] )
+//
+// One CTA per SM, 256 threads:
+//   warp 0      TMA producer (one lane)
+//   warp 1      MMA issuer   (one lane)
+//   warp 2      TMEM allocator / deallocator
+//   warps 4..7  epilogue: each owns TMEM lanes 32*(warp%4) .. +31 (one output row per thread)
+//
+// Tile = 128 x BN, BK = 64 bf16 (= one 128-byte swizzle row).  Both operand majors are supported
+// through the UMMA descriptors, so dgrad (B MN-major) and wgrad (A and B MN-major) need no
+// transposes in HBM.  Reference ops replaced: olmoasr/model.py:97-101 (Linear.forward) and its
+// autograd, model.py:768-770 (tied logits), model.py:592-593 (Conv1d after im2col).
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace oasr {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;               // 64 bf16 = 128 B = swizzle span
+constexpr int UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+
+struct GemmParams {
+  void* C;
+  void* C2;
+  const float* bias;
+  const void* aux;
+  int64_t ldc;
+  int64_t ldaux;
+  int M, N, K;
+  int tiles_m, tiles_n, splits;
+  int kblocks_total, kblocks_per_split;
+  int epi;
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + manual 1 KB alignment slack
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator buffers
+};
+
+__device__ __forceinline__ void store_bf16x32(bf16* dst, const float (&x)[32], int nvalid, bool vec) {
+  if (vec && nvalid == 32) {
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 u;
+      u.x = pack_bf16x2(x[8 * q + 0], x[8 * q + 1]);
+      u.y = pack_bf16x2(x[8 * q + 2], x[8 * q + 3]);
+      u.z = pack_bf16x2(x[8 * q + 4], x[8 * q + 5]);
+      u.w = pack_bf16x2(x[8 * q + 6], x[8 * q + 7]);
+      d4[q] = u;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < nvalid) dst[j] = __float2bfloat16_rn(x[j]);
+  }
+}
+
+__device__ __forceinline__ void load_bf16x32(const bf16* src, float (&x)[32], int nvalid, bool vec) {
+  if (vec && nvalid == 32) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 u = s4[q];
+      float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+      x[8 * q + 0] = a.x; x[8 * q + 1] = a.y; x[8 * q + 2] = b.x; x[8 * q + 3] = b.y;
+      x[8 * q + 4] = c.x; x[8 * q + 5] = c.y; x[8 * q + 6] = d.x; x[8 * q + 7] = d.y;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] = (j < nvalid) ? __bfloat162float(src[j]) : 0.f;
+  }
+}
+
+template <int BN, int A_MN, int B_MN>
+__global__ void __launch_bounds__(256, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmParams p) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[STAGES];
+  __shared__ __align__(8) uint64_t bar_empty[STAGES];
+  __shared__ __align__(8) uint64_t bar_tmem_full[2];
+  __shared__ __align__(8) uint64_t bar_tmem_empty[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::tma_prefetch_desc(&tmA);
+    ptx::tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&bar_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bar_empty[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&bar_tmem_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bar_tmem_empty[s]), 4);  // one arrive per epilogue warp
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc<C::TMEM_COLS>(ptx::smem_u32(&tmem_base_slot));
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  const int num_tiles = p.tiles_m * p.tiles_n * p.splits;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_blk = tile % p.tiles_n;
+        const int m_blk = (tile / p.tiles_n) % p.tiles_m;
+        const int split = tile / (p.tiles_n * p.tiles_m);
+        const int kb0 = split * p.kblocks_per_split;
+        const int kb1 = min(kb0 + p.kblocks_per_split, p.kblocks_total);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(ptx::smem_u32(&bar_empty[stage]), phase ^ 1);
+          const uint32_t full = ptx::smem_u32(&bar_full[stage]);
+          ptx::mbar_arrive_expect_tx(full, C::STAGE_BYTES);
+          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t sb = sa + A_STAGE_BYTES;
+          if (A_MN) {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i)
+              ptx::tma_load_2d(sa + i * (BK * 128), &tmA, full, m_blk * BM + i * 64, kb * BK);
+          } else {
+            ptx::tma_load_2d(sa, &tmA, full, kb * BK, m_blk * BM);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              ptx::tma_load_2d(sb + i * (BK * 128), &tmB, full, n_blk * BN + i * 64, kb * BK);
+          } else {
+            ptx::tma_load_2d(sb, &tmB, full, kb * BK, n_blk * BN);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, A_MN, B_MN);
+      // K-major  : 8-row groups 1024 B apart (SBO); LBO unused for swizzled K-major (CUTLASS sets 1)
+      // MN-major : 64-element MN chunks BK*128 B apart (LBO); 8-k groups 1024 B apart (SBO)
+      constexpr uint32_t a_lbo = A_MN ? BK * 128 : 16, a_sbo = 1024;
+      constexpr uint32_t b_lbo = B_MN ? BK * 128 : 16, b_sbo = 1024;
+      constexpr uint32_t a_kstep = A_MN ? UMMA_K * 128 : UMMA_K * 2;  // bytes per UMMA_K advance
+      constexpr uint32_t b_kstep = B_MN ? UMMA_K * 128 : UMMA_K * 2;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int split = tile / (p.tiles_n * p.tiles_m);
+        const int kb0 = split * p.kblocks_per_split;
+        const int kb1 = min(kb0 + p.kblocks_per_split, p.kblocks_total);
+        ptx::mbar_wait(ptx::smem_u32(&bar_tmem_empty[acc]), acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(ptx::smem_u32(&bar_full[stage]), phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t ad = ptx::umma_smem_desc_sw128(sa + k * a_kstep, a_lbo, a_sbo);
+            const uint64_t bd = ptx::umma_smem_desc_sw128(sb + k * b_kstep, b_lbo, b_sbo);
+            ptx::tc_mma_f16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          ptx::tc_commit(ptx::smem_u32(&bar_empty[stage]));  // frees the smem slot when MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        ptx::tc_commit(ptx::smem_u32(&bar_tmem_full[acc]));  // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;            // TMEM lane quarter this warp may touch
+    const int row_in_tile = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool c_is_f32 = (p.epi == OASR_EPI_F32 || p.epi == OASR_EPI_F32_ATOMIC_ADD);
+    const bool vec_c = c_is_f32 ? ((p.ldc & 3) == 0) : ((p.ldc & 7) == 0);
+    const bool vec_aux = (p.ldaux & 7) == 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_blk = tile % p.tiles_n;
+      const int m_blk = (tile / p.tiles_n) % p.tiles_m;
+      const int row = m_blk * BM + row_in_tile;
+      const bool row_ok = row < p.M;
+      ptx::mbar_wait(ptx::smem_u32(&bar_tmem_full[acc]), acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent `continue`
+        ptx::tc_ld_32x32b_x32(t_row + c * 32, r);
+        ptx::tc_wait_ld();
+        const int col = n_blk * BN + c * 32;
+        const int nvalid = min(32, p.N - col);
+        if (!row_ok || nvalid <= 0) continue;
+        float x[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]);
+        if (p.bias != nullptr) {
+          if (c_is_f32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) x[j] += __ldg(p.bias + col + j);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) x[j] += bf16_round(__ldg(p.bias + col + j));
+          }
+        }
+        const int64_t off = static_cast<int64_t>(row) * p.ldc + col;
+        switch (p.epi) {
+          case OASR_EPI_BF16:
+            store_bf16x32(reinterpret_cast<bf16*>(p.C) + off, x, nvalid, vec_c);
+            break;
+          case OASR_EPI_BF16_GELU: {
+            float g[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { x[j] = bf16_round(x[j]); g[j] = gelu_erf(x[j]); }
+            store_bf16x32(reinterpret_cast<bf16*>(p.C) + off, x, nvalid, vec_c);
+            store_bf16x32(reinterpret_cast<bf16*>(p.C2) + off, g, nvalid, vec_c);
+            break;
+          }
+          case OASR_EPI_BF16_RESIDUAL: {
+            float a[32];
+            load_bf16x32(reinterpret_cast<const bf16*>(p.aux) + static_cast<int64_t>(row) * p.ldaux + col,
+                         a, nvalid, vec_aux);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = a[j] + bf16_round(x[j]);
+            store_bf16x32(reinterpret_cast<bf16*>(p.C) + off, x, nvalid, vec_c);
+            break;
+          }
+          case OASR_EPI_BF16_GELU_BWD: {
+            float a[32];
+            load_bf16x32(reinterpret_cast<const bf16*>(p.aux) + static_cast<int64_t>(row) * p.ldaux + col,
+                         a, nvalid, vec_aux);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = bf16_round(x[j]) * gelu_erf_grad(a[j]);
+            store_bf16x32(reinterpret_cast<bf16*>(p.C) + off, x, nvalid, vec_c);
+            break;
+          }
+          case OASR_EPI_F32: {
+            float* dst = reinterpret_cast<float*>(p.C) + off;
+            if (vec_c && nvalid == 32) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                reinterpret_cast<float4*>(dst)[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nvalid) dst[j] = x[j];
+            }
+            break;
+          }
+          case OASR_EPI_F32_ATOMIC_ADD: {
+            float* dst = reinterpret_cast<float*>(p.C) + off;
+            if (vec_c && nvalid == 32) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                             ::"l"(dst + 4 * j), "f"(x[4 * j]), "f"(x[4 * j + 1]), "f"(x[4 * j + 2]),
+                               "f"(x[4 * j + 3])
+                             : "memory");
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nvalid) atomicAdd(dst + j, x[j]);
+            }
+            break;
+          }
+          default:
+            break;
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_tmem_empty[acc]));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int BN, int A_MN, int B_MN>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
+  using C = Cfg<BN>;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    OASR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = p.tiles_m * p.tiles_n * p.splits;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, 256, C::SMEM_BYTES, st>>>(tmA, tmB, p);
+  OASR_LAUNCH_CHECK();
+  return OASR_OK;
+}
+
+template <int BN>
+int dispatch_major(int a_mn, int b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                   const GemmParams& p, cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch<BN, 0, 0>(tmA, tmB, p, st);
+  if (!a_mn && b_mn) return launch<BN, 0, 1>(tmA, tmB, p, st);
+  if (a_mn && b_mn) return launch<BN, 1, 1>(tmA, tmB, p, st);
+  return launch<BN, 1, 0>(tmA, tmB, p, st);
+}
+
+}  // namespace
+}  // namespace oasr
+
+using namespace oasr;
+
+extern "C" int oasr_gemm_bf16(const void* A, int64_t lda, int a_layout, const void* B, int64_t ldb,
+                              int b_layout, void* Cout, int64_t ldc, void* C2, const float* bias,
+                              const void* aux, int64_t ldaux, int64_t M, int64_t N, int64_t K,
+                              int epilogue, int split_k, int block_n, void* stream) {
+  OASR_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%ld N=%ld K=%ld", (long)M, (long)N, (long)K);
+  OASR_REQUIRE(A && B && Cout, "gemm: null operand");
+  OASR_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
+               "gemm: A/B must be 16-byte aligned");
+  OASR_REQUIRE((lda & 7) == 0 && (ldb & 7) == 0, "gemm: lda/ldb must be multiples of 8 elements (TMA)");
+  OASR_REQUIRE(epilogue >= OASR_EPI_BF16 && epilogue <= OASR_EPI_F32_ATOMIC_ADD, "gemm: bad epilogue %d", epilogue);
+  OASR_REQUIRE(a_layout == OASR_K_MAJOR || a_layout == OASR_MN_MAJOR, "gemm: bad a_layout");
+  OASR_REQUIRE(b_layout == OASR_K_MAJOR || b_layout == OASR_MN_MAJOR, "gemm: bad b_layout");
+  if (epilogue == OASR_EPI_BF16_GELU) OASR_REQUIRE(C2 != nullptr, "gemm: GELU epilogue needs C2");
+  if (epilogue == OASR_EPI_BF16_RESIDUAL || epilogue == OASR_EPI_BF16_GELU_BWD)
+    OASR_REQUIRE(aux != nullptr, "gemm: epilogue %d needs aux", epilogue);
+  if (split_k < 1) split_k = 1;
+  OASR_REQUIRE(split_k == 1 || epilogue == OASR_EPI_F32_ATOMIC_ADD, "gemm: split_k needs the atomic-add epilogue");
+  if (block_n == 0) block_n = (N >= 256) ? 256 : (N > 64 ? 128 : 64);
+  OASR_REQUIRE(block_n == 64 || block_n == 128 || block_n == 256, "gemm: block_n must be 64/128/256");
+
+  GemmParams p;
+  p.C = Cout; p.C2 = C2; p.bias = bias; p.aux = aux; p.ldc = ldc; p.ldaux = ldaux;
+  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.tiles_m = (int)ceil_div(M, BM);
+  p.tiles_n = (int)ceil_div(N, block_n);
+  p.kblocks_total = (int)ceil_div(K, BK);
+  if (split_k > p.kblocks_total) split_k = p.kblocks_total;
+  p.kblocks_per_split = (int)ceil_div(p.kblocks_total, split_k);
+  p.splits = (int)ceil_div(p.kblocks_total, p.kblocks_per_split);
+  p.epi = epilogue;
+
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (a_layout == OASR_K_MAJOR)
+    rc = make_tmap_2d(&tmA, A, 2, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BK, BM, true);
+  else
+    rc = make_tmap_2d(&tmA, A, 2, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64, BK, true);
+  if (rc) return rc;
+  if (b_layout == OASR_K_MAJOR)
+    rc = make_tmap_2d(&tmB, B, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BK, block_n, true);
+  else
+    rc = make_tmap_2d(&tmB, B, 2, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, BK, true);
+  if (rc) return rc;
+
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (block_n) {
+    case 256: return dispatch_major<256>(a_layout, b_layout, tmA, tmB, p, st);
+    case 128: return dispatch_major<128>(a_layout, b_layout, tmA, tmB, p, st);
+    default: return dispatch_major<64>(a_layout, b_layout, tmA, tmB, p, st);
+  }
+}
