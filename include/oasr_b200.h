@@ -66,6 +66,83 @@ OASR_API int oasr_gemm_bf16(const void* A, int64_t lda, int a_layout, const void
                    int64_t M, int64_t N, int64_t K, int epilogue, int split_k, int block_n,
                    void* stream);
 
+/* ---- log-mel front end ----------------------------------------------------------------------------
+ * Replaces whisper.audio.log_mel_spectrogram as called per sample on CPU DataLoader workers by
+ * AudioTextDataset.preprocess_audio (scripts/training/train_timestamps.py:196-214), eval.py:157-162 and
+ * olmoasr/transcribe.py:148.  wave: (batch, n_samples) f32 or int16 (int16 is scaled by 1/32768 like
+ * train_timestamps.py:196); out: (batch, n_mels, n_samples/160) f32; clip_max: (batch,) f32 scratch.
+ * window/cos_tab/sin_tab: 400 f32 each (Hann window, cos/sin(2 pi i/400)); filters: (n_mels, 201) f32 with
+ * non-zero column range [klo[m], khi[m]) per band.  The dynamic-range floor is per clip. */
+OASR_API int oasr_logmel(const void* wave, int in_is_int16, const float* window, const float* cos_tab,
+                         const float* sin_tab, const float* filters, const int* klo, const int* khi, float* out,
+                         float* clip_max, int64_t batch, int64_t n_samples, int64_t n_mels, void* stream);
+
+/* ---- LayerNorm (olmoasr/model.py:25-39: F.layer_norm(x.float()).type(x.dtype)) -------------------
+ * x, y, dy, dx, dresidual: (rows, d) bf16; weight/bias/dweight/dbias: (d,) f32; mean/rstd: (rows,) f32
+ * (nullable in the forward).  Backward: dx = bf16(dresidual + bf16(dx_ln)) when dresidual != NULL;
+ * dweight/dbias are ACCUMULATED (+=) with atomics: zero them first. */
+OASR_API int oasr_layernorm_fwd(const void* x, const float* weight, const float* bias, void* y, float* mean,
+                                float* rstd, int64_t rows, int64_t d, float eps, void* stream);
+OASR_API int oasr_layernorm_bwd(const void* dy, const void* x, const float* weight, const float* mean,
+                                const float* rstd, const void* dresidual, void* dx, float* dweight, float* dbias,
+                                int64_t rows, int64_t d, void* stream);
+
+/* ---- attention (head_dim 64) ----------------------------------------------------------------------
+ * Replaces F.scaled_dot_product_attention in MultiHeadAttention.forward (olmoasr/model.py:331-340) and its
+ * autograd.  q: (B*Tq, ldq) bf16 with head h at columns [64h, 64h+64); k, v: (B*Tkv, ld*) likewise; o like q.
+ * causal != 0 applies key <= query; kv_len (B,) int32 (nullable) hides keys >= kv_len[b] -- together they are
+ * the reference's `padding_mask + causal mask` (model.py:740-743, train_timestamps.py:314-315).
+ * lse: (B,H,Tq) f32, log2 domain: log2(sum_k 2^(s_k * scale * log2 e)).
+ * Backward: delta (B,H,Tq) f32 and dq_accum (B*Tq, H*64) f32 are scratch. */
+OASR_API int oasr_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                void* o, int64_t ldo, float* lse, int64_t B, int64_t H, int64_t Tq, int64_t Tkv,
+                                int64_t head_dim, int causal, const int32_t* kv_len, float scale, void* stream);
+OASR_API int oasr_attention_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                const void* o, int64_t ldo, const void* dout, int64_t lddo, const float* lse,
+                                float* delta, float* dq_accum, void* dq, int64_t lddq, void* dk, int64_t lddk,
+                                void* dv, int64_t lddv, int64_t B, int64_t H, int64_t Tq, int64_t Tkv,
+                                int64_t head_dim, int causal, const int32_t* kv_len, float scale, void* stream);
+
+/* ---- token cross-entropy over bf16 logits ---------------------------------------------------------
+ * Replaces F.cross_entropy(logits.view(-1,V), y.view(-1), ignore_index) (train_timestamps.py:1444-1448).
+ * logits: (rows, ld) bf16, first V columns valid.  Forward writes lse (rows,) f32 (natural log) and ADDS
+ * [sum of row losses, number of non-ignored rows] into loss_sum_count[2] (zero it first).  Backward
+ * overwrites logits in place with bf16(grad_out / count * (softmax - onehot)); ignored rows become zero. */
+OASR_API int oasr_ce_fwd(const void* logits, const int64_t* targets, float* lse, float* loss_sum_count,
+                         int64_t rows, int64_t V, int64_t ld, int64_t ignore_index, void* stream);
+OASR_API int oasr_ce_bwd(void* logits, const int64_t* targets, const float* lse, const float* loss_sum_count,
+                         const float* grad_out, int64_t rows, int64_t V, int64_t ld, int64_t ignore_index,
+                         void* stream);
+/* `.float()` of model.py:770 for callers that ask for logits: (rows, ld) bf16 -> (rows, V) f32 */
+OASR_API int oasr_logits_to_f32(const void* src, float* dst, int64_t rows, int64_t V, int64_t ld, void* stream);
+
+/* ---- embedding (model.py:728-732) and its autograd (nn.Embedding padding_idx, model.py:665-667) ----
+ * out[b,s,:] = bf16(emb[ids[b,s]] + pos[pos_offset + s]);  backward ACCUMULATES into demb / dpos. */
+OASR_API int oasr_embed_fwd(const int64_t* ids, const float* emb, const float* pos, void* out, int64_t batch,
+                            int64_t S, int64_t d, int64_t pos_offset, int64_t n_rows_emb, void* stream);
+OASR_API int oasr_embed_bwd(const int64_t* ids, const void* dx, float* demb, float* dpos, int64_t batch, int64_t S,
+                            int64_t d, int64_t padding_idx, int64_t n_rows_emb, void* stream);
+
+/* ---- casts / conv-stem data movement / small reductions --------------------------------------------
+ * cast_f32_to_bf16: the per-call `weight.to(x.dtype)` of Linear.forward (model.py:97-101), hoisted.
+ * cast_conv_weight: Conv1d weight (C_out, C_in, 3) f32 -> (C_out, 3, C_in) bf16 (model.py:193-195) so that
+ *   conv = im2col + GEMM; unpermute_conv_wgrad is the inverse for the fp32 weight gradient.
+ * im2col_conv1: mel (B, C, T) f32 -> (B*T, kpad) bf16, A[b,t][k*C+c] = mel[b][c][t+k-1]        (model.py:592)
+ * im2col_conv2: h (B, T_in, d) bf16 -> (B*T_out, 3d) bf16, rows 2t-1, 2t, 2t+1 (stride 2, pad 1) (model.py:593)
+ * col2im_conv2_gelu_bwd: gradient w.r.t. conv2's input gathered back and multiplied by gelu'(pre1)
+ * add_pos: (x + positional_embedding).to(x.dtype)                                              (model.py:602)
+ * gelu_bwd: dy * gelu_erf'(pre);  colsum_bf16: db[n] += sum_m dy[m,n] (bias gradients, ACCUMULATES). */
+OASR_API int oasr_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+OASR_API int oasr_cast_conv_weight(const float* src, void* dst, int64_t c_out, int64_t c_in, void* stream);
+OASR_API int oasr_unpermute_conv_wgrad(const float* src, float* dst, int64_t c_out, int64_t c_in, void* stream);
+OASR_API int oasr_im2col_conv1(const float* mel, void* A, int64_t batch, int64_t C, int64_t T, int64_t kpad, void* stream);
+OASR_API int oasr_im2col_conv2(const void* h, void* A, int64_t batch, int64_t T_in, int64_t T_out, int64_t d, void* stream);
+OASR_API int oasr_col2im_conv2_gelu_bwd(const void* dA, const void* pre1, void* dpre1, int64_t batch, int64_t T_in,
+                                        int64_t T_out, int64_t d, void* stream);
+OASR_API int oasr_add_pos(const void* x, const float* pos, void* out, int64_t rows, int64_t T, int64_t d, void* stream);
+OASR_API int oasr_gelu_bwd(const void* dy, const void* pre, void* out, int64_t n, void* stream);
+OASR_API int oasr_colsum_bf16(const void* dy, float* db, int64_t M, int64_t N, int64_t ld, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,30 @@ class OasrError(RuntimeError):
 _SIGNATURES = {
     "oasr_abi_version": [],
     "oasr_device_sm_count": [],
+    "oasr_logmel": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                    c_i64, c_i64, c_i64, c_void_p],
+    "oasr_layernorm_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_float, c_void_p],
+    "oasr_layernorm_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                           c_i64, c_i64, c_void_p],
+    "oasr_attention_fwd": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p,
+                           c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_void_p, c_float, c_void_p],
+    "oasr_attention_bwd": [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64,
+                           c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64,
+                           c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_void_p, c_float, c_void_p],
+    "oasr_ce_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_void_p],
+    "oasr_ce_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_void_p],
+    "oasr_logits_to_f32": [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p],
+    "oasr_embed_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_void_p],
+    "oasr_embed_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_void_p],
+    "oasr_cast_f32_to_bf16": [c_void_p, c_void_p, c_i64, c_void_p],
+    "oasr_cast_conv_weight": [c_void_p, c_void_p, c_i64, c_i64, c_void_p],
+    "oasr_unpermute_conv_wgrad": [c_void_p, c_void_p, c_i64, c_i64, c_void_p],
+    "oasr_im2col_conv1": [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_void_p],
+    "oasr_im2col_conv2": [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_void_p],
+    "oasr_col2im_conv2_gelu_bwd": [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_void_p],
+    "oasr_add_pos": [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p],
+    "oasr_gelu_bwd": [c_void_p, c_void_p, c_void_p, c_i64, c_void_p],
+    "oasr_colsum_bf16": [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p],
     "oasr_gemm_bf16": [c_void_p, c_i64, c_int, c_void_p, c_i64, c_int, c_void_p, c_i64, c_void_p, c_void_p,
                        c_void_p, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_void_p],
 }

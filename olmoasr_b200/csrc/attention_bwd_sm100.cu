@@ -1,0 +1,367 @@
+// Flash-style attention backward for head_dim 64 on tcgen05 / TMEM (sm_100a).
+//
+// Autograd of F.scaled_dot_product_attention (olmoasr/model.py:331-340) for the three training uses
+// (encoder self, decoder causal+length self, cross).  Given Q, K, V, O, dO and the forward's log2-domain
+// LSE it produces dQ, dK, dV without ever materialising the (Tq x Tkv) score matrix in HBM.
+//
+// CTA = one 128-key tile of one (b, h); loops over the 128-query tiles that can see it:
+//     S  = Q K^T            dP = dO V^T                      (tcgen05, accumulators in TMEM)
+//     P  = exp2(S c - LSE)  dS = P o (dP - D)                (thread r owns query row r: no reductions)
+//     dV += P^T dO          dK += dS^T Q        dQ_i = dS K  (P / dS go through swizzled smem as bf16;
+//                                                             the "transposes" are MN-major descriptors)
+// dV and dK stay resident in TMEM for the whole loop; dQ_i is drained per query tile and reduced across
+// key tiles with vectorised fp32 red.global.add into a scratch buffer (converted to bf16 afterwards).
+// TMEM map (512 cols): S 0..127 | dP 128..255 | dV 256..319 | dK 320..383 | dQ 384..447.
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace oasr {
+namespace {
+
+constexpr int HD = 64;
+constexpr int BQ = 128;
+constexpr int BKV = 128;
+constexpr int TILE_BYTES = 128 * HD * 2;  // 16 KB
+constexpr int P_BYTES = BQ * BKV * 2;     // 32 KB
+// K, V, Q[2], dO[2], P, dS
+constexpr int BWD_TILES = 2 * TILE_BYTES + 4 * TILE_BYTES + 2 * P_BYTES;  // 160 KB
+constexpr int BWD_SMEM = BWD_TILES + 128;
+constexpr int TMEM_COLS = 512;
+constexpr int S_COL = 0, DP_COL = 128, DV_COL = 256, DK_COL = 320, DQ_COL = 384;
+
+struct BwdParams {
+  const float* lse;   // (B,H,Tq) log2 domain
+  const float* delta; // (B,H,Tq) rowsum(dO o O)
+  float* dq_accum;    // (B*Tq, H*64) fp32, zero-initialised
+  bf16* dk;
+  bf16* dv;
+  const int32_t* kv_len;
+  int64_t lddk, lddv;
+  int B, H, Tq, Tkv;
+  int causal;
+  float scale, scale_log2;
+};
+
+__device__ __forceinline__ void store_swizzled_row32(uint32_t tile_base, int r, int cc, const float (&x)[32]) {
+  // 32 consecutive bf16 columns [cc*32, cc*32+32) of row r into a two-half [128][128B] swizzled tile
+  const uint32_t half_base = tile_base + (cc >> 1) * (P_BYTES / 2) + r * 128;
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) {
+    const int chunk = (cc & 1) * 4 + q4;
+    const uint32_t addr = half_base + ((chunk ^ (r & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                 "r"(pack_bf16x2(x[8 * q4 + 0], x[8 * q4 + 1])), "r"(pack_bf16x2(x[8 * q4 + 2], x[8 * q4 + 3])),
+                 "r"(pack_bf16x2(x[8 * q4 + 4], x[8 * q4 + 5])), "r"(pack_bf16x2(x[8 * q4 + 6], x[8 * q4 + 7]))
+                 : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(192, 1)
+attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                     const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + BWD_TILES);
+  uint64_t& bar_kv = bars[0];
+  uint64_t& bar_sdp = bars[1];
+  uint64_t& bar_pds = bars[2];
+  uint64_t& bar_dq = bars[3];
+  uint64_t& bar_done = bars[4];
+  uint64_t* bar_q_full = bars + 5;
+  uint64_t* bar_q_empty = bars + 7;
+  uint32_t& tmem_slot = *reinterpret_cast<uint32_t*>(bars + 9);
+
+  const uint32_t sbase = ptx::smem_u32(smem_raw);
+  if ((sbase & 1023u) != 0) {
+    if (threadIdx.x == 0) printf("oasr attention_bwd: dynamic smem base %u not 1 KB aligned\n", sbase);
+    __trap();
+  }
+  const uint32_t sK = sbase, sV = sK + TILE_BYTES;
+  const uint32_t sQ0 = sV + TILE_BYTES;            // stage s: Q at sQ0 + s*32K, dO right after
+  const uint32_t sP = sQ0 + 4 * TILE_BYTES, sdS = sP + P_BYTES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kv_tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int kv0 = kv_tile * BKV;
+
+  int kv_valid = p.Tkv;
+  if (p.kv_len) kv_valid = min(kv_valid, max(1, p.kv_len[b]));
+  const int n_q_tiles = (p.Tq + BQ - 1) / BQ;
+  const int i_begin = p.causal ? kv_tile : 0;
+  const int i_end = (kv0 < kv_valid) ? n_q_tiles : i_begin;  // fully masked key tile: no work, zero grads
+  const int n_iter = i_end - i_begin;
+
+  if (warp == 0 && lane == 0) {
+    ptx::tma_prefetch_desc(&tmQ); ptx::tma_prefetch_desc(&tmK); ptx::tma_prefetch_desc(&tmV); ptx::tma_prefetch_desc(&tmdO);
+    ptx::mbar_init(ptx::smem_u32(&bar_kv), 1);
+    ptx::mbar_init(ptx::smem_u32(&bar_sdp), 1);
+    ptx::mbar_init(ptx::smem_u32(&bar_pds), 4);
+    ptx::mbar_init(ptx::smem_u32(&bar_dq), 1);
+    ptx::mbar_init(ptx::smem_u32(&bar_done), 1);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&bar_q_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bar_q_empty[s]), 1);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc<TMEM_COLS>(ptx::smem_u32(&tmem_slot));
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0 && n_iter > 0) {
+      ptx::mbar_arrive_expect_tx(ptx::smem_u32(&bar_kv), 2 * TILE_BYTES);
+      ptx::tma_load_2d(sK, &tmK, ptx::smem_u32(&bar_kv), h * HD, b * p.Tkv + kv0);
+      ptx::tma_load_2d(sV, &tmV, ptx::smem_u32(&bar_kv), h * HD, b * p.Tkv + kv0);
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it & 1;
+        ptx::mbar_wait(ptx::smem_u32(&bar_q_empty[s]), ((it >> 1) & 1) ^ 1);
+        const uint32_t full = ptx::smem_u32(&bar_q_full[s]);
+        ptx::mbar_arrive_expect_tx(full, 2 * TILE_BYTES);
+        const int qrow = b * p.Tq + (i_begin + it) * BQ;
+        ptx::tma_load_2d(sQ0 + s * 2 * TILE_BYTES, &tmQ, full, h * HD, qrow);
+        ptx::tma_load_2d(sQ0 + s * 2 * TILE_BYTES + TILE_BYTES, &tmdO, full, h * HD, qrow);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_iter > 0) {
+      constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, 128, 0, 0);    // S, dP
+      constexpr uint32_t idesc_kv = ptx::umma_idesc_bf16(128, 64, 1, 1);    // dV, dK
+      constexpr uint32_t idesc_dq = ptx::umma_idesc_bf16(128, 64, 0, 1);    // dQ
+      auto issue_s_dp = [&](int it) {
+        const uint32_t sQ = sQ0 + (it & 1) * 2 * TILE_BYTES, sdO = sQ + TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          ptx::tc_mma_f16(tmem + S_COL, ptx::umma_smem_desc_sw128(sQ + k * 32, 16, 1024),
+                          ptx::umma_smem_desc_sw128(sK + k * 32, 16, 1024), idesc_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          ptx::tc_mma_f16(tmem + DP_COL, ptx::umma_smem_desc_sw128(sdO + k * 32, 16, 1024),
+                          ptx::umma_smem_desc_sw128(sV + k * 32, 16, 1024), idesc_s, k > 0);
+        ptx::tc_commit(ptx::smem_u32(&bar_sdp));
+      };
+      ptx::mbar_wait(ptx::smem_u32(&bar_kv), 0);
+      ptx::mbar_wait(ptx::smem_u32(&bar_q_full[0]), 0);
+      ptx::tc_fence_after();
+      issue_s_dp(0);
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it & 1;
+        const uint32_t sQ = sQ0 + s * 2 * TILE_BYTES, sdO = sQ + TILE_BYTES;
+        ptx::mbar_wait(ptx::smem_u32(&bar_pds), it & 1);  // P, dS in smem; S/dP/dQ TMEM regions drained
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < BQ / 16; ++k) {  // reduction over the 128 query rows, 16 at a time
+          const uint64_t a_p = ptx::umma_smem_desc_sw128(sP + k * 2048, P_BYTES / 2, 1024);     // P^T  (MN-major A)
+          const uint64_t a_ds = ptx::umma_smem_desc_sw128(sdS + k * 2048, P_BYTES / 2, 1024);   // dS^T (MN-major A)
+          const uint64_t b_do = ptx::umma_smem_desc_sw128(sdO + k * 2048, BQ * 128, 1024);      // dO   (MN-major B)
+          const uint64_t b_q = ptx::umma_smem_desc_sw128(sQ + k * 2048, BQ * 128, 1024);        // Q    (MN-major B)
+          ptx::tc_mma_f16(tmem + DV_COL, a_p, b_do, idesc_kv, (it > 0 || k > 0) ? 1u : 0u);
+          ptx::tc_mma_f16(tmem + DK_COL, a_ds, b_q, idesc_kv, (it > 0 || k > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k)   // dQ_i = dS K : reduction over the 128 keys
+          ptx::tc_mma_f16(tmem + DQ_COL,
+                          ptx::umma_smem_desc_sw128(sdS + (k >> 2) * (P_BYTES / 2) + (k & 3) * 32, 16, 1024),
+                          ptx::umma_smem_desc_sw128(sK + k * 2048, BKV * 128, 1024), idesc_dq, k > 0);
+        ptx::tc_commit(ptx::smem_u32(&bar_dq));
+        ptx::tc_commit(ptx::smem_u32(&bar_q_empty[s]));
+        if (it + 1 < n_iter) {
+          ptx::mbar_wait(ptx::smem_u32(&bar_q_full[(it + 1) & 1]), ((it + 1) >> 1) & 1);
+          ptx::tc_fence_after();
+          issue_s_dp(it + 1);
+        }
+      }
+      ptx::tc_commit(ptx::smem_u32(&bar_done));
+    }
+  } else {
+    // ----------------------------- compute warps -----------------------------
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t t_lane = static_cast<uint32_t>(quarter * 32) << 16;
+    const float c = p.scale_log2;
+    for (int it = 0; it < n_iter; ++it) {
+      const int q0 = (i_begin + it) * BQ;
+      const int qi = q0 + r;
+      const bool q_ok = qi < p.Tq;
+      const int64_t stat_idx = (static_cast<int64_t>(b) * p.H + h) * p.Tq + qi;
+      const float lse = q_ok ? p.lse[stat_idx] : 0.f;
+      const float dlt = q_ok ? p.delta[stat_idx] : 0.f;
+      int limit = kv_valid - kv0;                     // visible keys of this tile: [0, limit)
+      if (p.causal) limit = min(limit, qi - kv0 + 1);
+      if (!q_ok) limit = 0;
+      ptx::mbar_wait(ptx::smem_u32(&bar_sdp), it & 1);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < BKV / 32; ++cc) {
+        uint32_t sv[32], dv[32];
+        ptx::tc_ld_32x32b_x32(tmem + t_lane + S_COL + cc * 32, sv);
+        ptx::tc_ld_32x32b_x32(tmem + t_lane + DP_COL + cc * 32, dv);
+        ptx::tc_wait_ld();
+        float pr[32], ds[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const bool vis = cc * 32 + i < limit;
+          const float pv = vis ? fast_exp2(__uint_as_float(sv[i]) * c - lse) : 0.f;
+          pr[i] = pv;
+          ds[i] = pv * (__uint_as_float(dv[i]) - dlt);
+        }
+        store_swizzled_row32(sP, r, cc, pr);
+        store_swizzled_row32(sdS, r, cc, ds);
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_pds));
+      // drain dQ_i
+      ptx::mbar_wait(ptx::smem_u32(&bar_dq), it & 1);
+      ptx::tc_fence_after();
+      float* dq_row = p.dq_accum + (static_cast<int64_t>(b) * p.Tq + qi) * (p.H * HD) + h * HD;
+#pragma unroll
+      for (int cc = 0; cc < HD / 32; ++cc) {
+        uint32_t v[32];
+        ptx::tc_ld_32x32b_x32(tmem + t_lane + DQ_COL + cc * 32, v);
+        ptx::tc_wait_ld();
+        if (q_ok) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                         ::"l"(dq_row + cc * 32 + 4 * j), "f"(__uint_as_float(v[4 * j]) * p.scale),
+                           "f"(__uint_as_float(v[4 * j + 1]) * p.scale), "f"(__uint_as_float(v[4 * j + 2]) * p.scale),
+                           "f"(__uint_as_float(v[4 * j + 3]) * p.scale)
+                         : "memory");
+        }
+      }
+      ptx::tc_fence_before();
+    }
+    // ---- dK / dV for key row r of this tile
+    const int ki = kv0 + r;
+    if (n_iter > 0) {
+      ptx::mbar_wait(ptx::smem_u32(&bar_done), 0);
+      ptx::tc_fence_after();
+    }
+    bf16* dk_row = p.dk + (static_cast<int64_t>(b) * p.Tkv + ki) * p.lddk + h * HD;
+    bf16* dv_row = p.dv + (static_cast<int64_t>(b) * p.Tkv + ki) * p.lddv + h * HD;
+#pragma unroll
+    for (int cc = 0; cc < HD / 32; ++cc) {
+      uint32_t a[32], bq[32];
+      if (n_iter > 0) {
+        ptx::tc_ld_32x32b_x32(tmem + t_lane + DV_COL + cc * 32, a);
+        ptx::tc_ld_32x32b_x32(tmem + t_lane + DK_COL + cc * 32, bq);
+        ptx::tc_wait_ld();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { a[i] = 0u; bq[i] = 0u; }
+      }
+      if (ki < p.Tkv) {
+#pragma unroll
+        for (int q8 = 0; q8 < 4; ++q8) {
+          uint4 u, w;
+          u.x = pack_bf16x2(__uint_as_float(a[8 * q8 + 0]), __uint_as_float(a[8 * q8 + 1]));
+          u.y = pack_bf16x2(__uint_as_float(a[8 * q8 + 2]), __uint_as_float(a[8 * q8 + 3]));
+          u.z = pack_bf16x2(__uint_as_float(a[8 * q8 + 4]), __uint_as_float(a[8 * q8 + 5]));
+          u.w = pack_bf16x2(__uint_as_float(a[8 * q8 + 6]), __uint_as_float(a[8 * q8 + 7]));
+          w.x = pack_bf16x2(__uint_as_float(bq[8 * q8 + 0]) * p.scale, __uint_as_float(bq[8 * q8 + 1]) * p.scale);
+          w.y = pack_bf16x2(__uint_as_float(bq[8 * q8 + 2]) * p.scale, __uint_as_float(bq[8 * q8 + 3]) * p.scale);
+          w.z = pack_bf16x2(__uint_as_float(bq[8 * q8 + 4]) * p.scale, __uint_as_float(bq[8 * q8 + 5]) * p.scale);
+          w.w = pack_bf16x2(__uint_as_float(bq[8 * q8 + 6]) * p.scale, __uint_as_float(bq[8 * q8 + 7]) * p.scale);
+          reinterpret_cast<uint4*>(dv_row + cc * 32)[q8] = u;
+          reinterpret_cast<uint4*>(dk_row + cc * 32)[q8] = w;
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<TMEM_COLS>(tmem);
+  }
+}
+
+// delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]   (one warp per (row, head): 64 elements, 2 per lane)
+__global__ void attention_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, float* __restrict__ delta,
+                                       int64_t ldo, int64_t lddo, int B, int H, int Tq) {
+  const int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t total = static_cast<int64_t>(B) * Tq * H;
+  if (w >= total) return;
+  const int h = w % H;
+  const int64_t row = w / H;  // b*Tq + q
+  const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(o + row * ldo + h * HD + lane * 2));
+  const float2 g = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dout + row * lddo + h * HD + lane * 2));
+  const float s = warp_sum(a.x * g.x + a.y * g.y);
+  if (lane == 0) {
+    const int b = row / Tq, q = row % Tq;
+    delta[(static_cast<int64_t>(b) * H + h) * Tq + q] = s;
+  }
+}
+
+// dq (bf16, row stride lddq) = bf16(dq_accum (fp32, contiguous rows of `width`))
+__global__ void f32_rows_to_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t rows, int width, int64_t ldd) {
+  const int vec_per_row = width >> 3;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < rows * vec_per_row;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = i / vec_per_row;
+    const int v = i % vec_per_row;
+    const float4 a = reinterpret_cast<const float4*>(src + row * width)[2 * v];
+    const float4 b2 = reinterpret_cast<const float4*>(src + row * width)[2 * v + 1];
+    uint4 u;
+    u.x = pack_bf16x2(a.x, a.y); u.y = pack_bf16x2(a.z, a.w);
+    u.z = pack_bf16x2(b2.x, b2.y); u.w = pack_bf16x2(b2.z, b2.w);
+    reinterpret_cast<uint4*>(dst + row * ldd)[v] = u;
+  }
+}
+
+}  // namespace
+}  // namespace oasr
+
+using namespace oasr;
+
+extern "C" int oasr_attention_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                  const void* o, int64_t ldo, const void* dout, int64_t lddo, const float* lse,
+                                  float* delta, float* dq_accum, void* dq, int64_t lddq, void* dk, int64_t lddk,
+                                  void* dv, int64_t lddv, int64_t B, int64_t H, int64_t Tq, int64_t Tkv,
+                                  int64_t head_dim, int causal, const int32_t* kv_len, float scale, void* stream) {
+  OASR_REQUIRE(head_dim == HD, "attention_bwd: head_dim %ld unsupported", (long)head_dim);
+  OASR_REQUIRE(B > 0 && H > 0 && Tq > 0 && Tkv > 0, "attention_bwd: empty problem");
+  OASR_REQUIRE(((ldq | ldk | ldv | ldo | lddo | lddq | lddk | lddv) & 7) == 0, "attention_bwd: strides must be multiples of 8");
+  OASR_REQUIRE(!causal || Tq == Tkv, "attention_bwd: causal needs Tq == Tkv");
+  cudaStream_t st = (cudaStream_t)stream;
+  CUtensorMap tmQ, tmK, tmV, tmdO;
+  int rc;
+  if ((rc = make_tmap_2d(&tmQ, q, 2, (uint64_t)(H * HD), (uint64_t)(B * Tq), (uint64_t)ldq * 2, HD, BQ, true))) return rc;
+  if ((rc = make_tmap_2d(&tmK, k, 2, (uint64_t)(H * HD), (uint64_t)(B * Tkv), (uint64_t)ldk * 2, HD, BKV, true))) return rc;
+  if ((rc = make_tmap_2d(&tmV, v, 2, (uint64_t)(H * HD), (uint64_t)(B * Tkv), (uint64_t)ldv * 2, HD, BKV, true))) return rc;
+  if ((rc = make_tmap_2d(&tmdO, dout, 2, (uint64_t)(H * HD), (uint64_t)(B * Tq), (uint64_t)lddo * 2, HD, BQ, true))) return rc;
+
+  const int64_t n_warps = B * Tq * H;
+  attention_delta_kernel<<<(unsigned)ceil_div(n_warps * 32, 256), 256, 0, st>>>((const bf16*)o, (const bf16*)dout, delta, ldo, lddo,
+                                                                              (int)B, (int)H, (int)Tq);
+  OASR_LAUNCH_CHECK();
+  OASR_CUDA_OK(cudaMemsetAsync(dq_accum, 0, sizeof(float) * B * Tq * H * HD, st));
+
+  BwdParams p;
+  p.lse = lse; p.delta = delta; p.dq_accum = dq_accum; p.dk = (bf16*)dk; p.dv = (bf16*)dv; p.kv_len = kv_len;
+  p.lddk = lddk; p.lddv = lddv; p.B = (int)B; p.H = (int)H; p.Tq = (int)Tq; p.Tkv = (int)Tkv; p.causal = causal;
+  p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
+  static bool attr_set = false;
+  if (!attr_set) {
+    OASR_CUDA_OK(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)ceil_div(Tkv, BKV), (unsigned)H, (unsigned)B);
+  attention_bwd_kernel<<<grid, 192, BWD_SMEM, st>>>(tmQ, tmK, tmV, tmdO, p);
+  OASR_LAUNCH_CHECK();
+  const int64_t rows = B * Tq;
+  int64_t blocks = ceil_div(rows * (H * HD / 8), 256);
+  const int64_t cap = (int64_t)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  f32_rows_to_bf16_kernel<<<(unsigned)blocks, 256, 0, st>>>(dq_accum, (bf16*)dq, rows, (int)(H * HD), lddq);
+  OASR_LAUNCH_CHECK();
+  return OASR_OK;
+}

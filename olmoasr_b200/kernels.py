@@ -46,3 +46,174 @@ def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, out=None, out2=None, bias=Non
     if epi == EPI_BF16_GELU:
         return out, out2
     return out
+
+
+# ----------------------------------------------------------------------------------------------------
+def _bf16_2d(t, name):
+    _req(t.is_cuda and t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1, f"{name}: 2-D bf16 CUDA tensor, unit inner stride")
+
+
+def layernorm_fwd(x, weight, bias, eps=1e-5, want_stats=True):
+    """x (rows, d) bf16 contiguous -> y bf16 [, mean, rstd f32].  model.py:25-39."""
+    _bf16_2d(x, "layernorm x")
+    _req(x.is_contiguous() and weight.dtype == torch.float32 and bias.dtype == torch.float32, "layernorm: contiguous x, f32 params")
+    rows, d = x.shape
+    y = torch.empty_like(x)
+    mean = rstd = None
+    if want_stats:
+        mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+    call("oasr_layernorm_fwd", ptr(x), ptr(weight), ptr(bias), ptr(y), ptr(mean), ptr(rstd), rows, d, eps, stream())
+    return (y, mean, rstd) if want_stats else y
+
+
+def layernorm_bwd(dy, x, weight, mean, rstd, dweight, dbias, dresidual=None):
+    """Returns dx = bf16(dresidual + bf16(dx_ln)); accumulates into dweight / dbias (f32)."""
+    _bf16_2d(dy, "layernorm dy"); _bf16_2d(x, "layernorm x")
+    _req(dy.is_contiguous() and x.is_contiguous() and (dresidual is None or dresidual.is_contiguous()), "layernorm_bwd: contiguous")
+    rows, d = x.shape
+    dx = torch.empty_like(x)
+    call("oasr_layernorm_bwd", ptr(dy), ptr(x), ptr(weight), ptr(mean), ptr(rstd), ptr(dresidual), ptr(dx), ptr(dweight),
+         ptr(dbias), rows, d, stream())
+    return dx
+
+
+def attention_fwd(q, k, v, B, H, Tq, Tkv, causal=False, kv_len=None, scale=None, want_lse=True, out=None):
+    """q (B*Tq, >=H*64) bf16 view, k/v (B*Tkv, ...) views (column slices of fused projections are fine)."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _bf16_2d(t, n)
+    _req(q.shape[0] == B * Tq and k.shape[0] == B * Tkv and v.shape[0] == B * Tkv, "attention: row counts")
+    _req(q.shape[1] == H * 64 and k.shape[1] == H * 64 and v.shape[1] == H * 64, "attention: width must be H*64")
+    if scale is None:
+        scale = 64 ** -0.5
+    if out is None:
+        out = torch.empty((B * Tq, H * 64), device=q.device, dtype=torch.bfloat16)
+    lse = torch.empty((B, H, Tq), device=q.device, dtype=torch.float32) if want_lse else None
+    if kv_len is not None:
+        _req(kv_len.dtype == torch.int32 and kv_len.numel() == B, "attention: kv_len must be int32 (B,)")
+    call("oasr_attention_fwd", ptr(q), q.stride(0), ptr(k), k.stride(0), ptr(v), v.stride(0), ptr(out), out.stride(0),
+         ptr(lse), B, H, Tq, Tkv, 64, int(causal), ptr(kv_len), float(scale), stream())
+    return out, lse
+
+
+def attention_bwd(q, k, v, o, dout, lse, B, H, Tq, Tkv, causal=False, kv_len=None, scale=None, dq=None, dk=None, dv=None):
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (o, "o"), (dout, "dout")):
+        _bf16_2d(t, n)
+    if scale is None:
+        scale = 64 ** -0.5
+    dev = q.device
+    if dq is None:
+        dq = torch.empty((B * Tq, H * 64), device=dev, dtype=torch.bfloat16)
+    if dk is None:
+        dk = torch.empty((B * Tkv, H * 64), device=dev, dtype=torch.bfloat16)
+    if dv is None:
+        dv = torch.empty((B * Tkv, H * 64), device=dev, dtype=torch.bfloat16)
+    delta = torch.empty((B, H, Tq), device=dev, dtype=torch.float32)
+    dq_accum = torch.empty((B * Tq, H * 64), device=dev, dtype=torch.float32)
+    call("oasr_attention_bwd", ptr(q), q.stride(0), ptr(k), k.stride(0), ptr(v), v.stride(0), ptr(o), o.stride(0),
+         ptr(dout), dout.stride(0), ptr(lse), ptr(delta), ptr(dq_accum), ptr(dq), dq.stride(0), ptr(dk), dk.stride(0),
+         ptr(dv), dv.stride(0), B, H, Tq, Tkv, 64, int(causal), ptr(kv_len), float(scale), stream())
+    return dq, dk, dv
+
+
+def ce_fwd(logits, targets, V, ignore_index):
+    """logits (rows, ld) bf16; returns (lse (rows,), loss_sum_count (2,)) -- loss = lsc[0] / lsc[1]."""
+    _bf16_2d(logits, "ce logits")
+    rows = logits.shape[0]
+    _req(targets.dtype == torch.int64 and targets.numel() == rows and targets.is_contiguous(), "ce: targets int64 (rows,)")
+    lse = torch.empty(rows, device=logits.device, dtype=torch.float32)
+    lsc = torch.zeros(2, device=logits.device, dtype=torch.float32)
+    call("oasr_ce_fwd", ptr(logits), ptr(targets), ptr(lse), ptr(lsc), rows, V, logits.stride(0), ignore_index, stream())
+    return lse, lsc
+
+
+def ce_bwd_(logits, targets, lse, lsc, grad_out, V, ignore_index):
+    """In place: logits <- d(loss)/d(logits) as bf16."""
+    _req(grad_out.dtype == torch.float32 and grad_out.numel() == 1, "ce_bwd: grad_out must be one f32")
+    call("oasr_ce_bwd", ptr(logits), ptr(targets), ptr(lse), ptr(lsc), ptr(grad_out), logits.shape[0], V, logits.stride(0),
+         ignore_index, stream())
+    return logits
+
+
+def logits_to_f32(logits, V):
+    out = torch.empty((logits.shape[0], V), device=logits.device, dtype=torch.float32)
+    call("oasr_logits_to_f32", ptr(logits), ptr(out), logits.shape[0], V, logits.stride(0), stream())
+    return out
+
+
+def embed_fwd(ids, emb, pos, pos_offset=0):
+    _req(ids.dtype == torch.int64 and ids.dim() == 2 and ids.is_contiguous(), "embed: ids int64 (B,S)")
+    B, S = ids.shape
+    d = emb.shape[1]
+    out = torch.empty((B * S, d), device=emb.device, dtype=torch.bfloat16)
+    call("oasr_embed_fwd", ptr(ids), ptr(emb), ptr(pos), ptr(out), B, S, d, pos_offset, emb.shape[0], stream())
+    return out
+
+
+def embed_bwd(ids, dx, demb, dpos, padding_idx):
+    B, S = ids.shape
+    call("oasr_embed_bwd", ptr(ids), ptr(dx), ptr(demb), ptr(dpos), B, S, dx.shape[1], padding_idx, demb.shape[0], stream())
+
+
+def cast_bf16(src, dst=None):
+    _req(src.dtype == torch.float32 and src.is_contiguous(), "cast: f32 contiguous")
+    if dst is None:
+        dst = torch.empty(src.shape, device=src.device, dtype=torch.bfloat16)
+    call("oasr_cast_f32_to_bf16", ptr(src), ptr(dst), src.numel(), stream())
+    return dst
+
+
+def cast_conv_weight(w, dst=None):
+    c_out, c_in, k = w.shape
+    _req(k == 3 and w.is_contiguous() and w.dtype == torch.float32, "conv weight (C_out, C_in, 3) f32")
+    if dst is None:
+        dst = torch.empty((c_out, 3 * c_in), device=w.device, dtype=torch.bfloat16)
+    call("oasr_cast_conv_weight", ptr(w), ptr(dst), c_out, c_in, stream())
+    return dst
+
+
+def unpermute_conv_wgrad(g, c_out, c_in):
+    out = torch.empty((c_out, c_in, 3), device=g.device, dtype=torch.float32)
+    call("oasr_unpermute_conv_wgrad", ptr(g), ptr(out), c_out, c_in, stream())
+    return out
+
+
+def im2col_conv1(mel, kpad):
+    B, C, T = mel.shape
+    _req(mel.dtype == torch.float32 and mel.is_contiguous(), "mel f32 contiguous")
+    A = torch.empty((B * T, kpad), device=mel.device, dtype=torch.bfloat16)
+    call("oasr_im2col_conv1", ptr(mel), ptr(A), B, C, T, kpad, stream())
+    return A
+
+
+def im2col_conv2(h, B, T_in, d):
+    T_out = (T_in + 2 - 3) // 2 + 1
+    A = torch.empty((B * T_out, 3 * d), device=h.device, dtype=torch.bfloat16)
+    call("oasr_im2col_conv2", ptr(h), ptr(A), B, T_in, T_out, d, stream())
+    return A
+
+
+def col2im_conv2_gelu_bwd(dA, pre1, B, T_in, T_out, d):
+    out = torch.empty((B * T_in, d), device=dA.device, dtype=torch.bfloat16)
+    call("oasr_col2im_conv2_gelu_bwd", ptr(dA), ptr(pre1), ptr(out), B, T_in, T_out, d, stream())
+    return out
+
+
+def add_pos(x, pos, T):
+    out = torch.empty_like(x)
+    call("oasr_add_pos", ptr(x), ptr(pos), ptr(out), x.shape[0], T, x.shape[1], stream())
+    return out
+
+
+def gelu_bwd(dy, pre):
+    out = torch.empty_like(dy)
+    call("oasr_gelu_bwd", ptr(dy), ptr(pre), ptr(out), dy.numel(), stream())
+    return out
+
+
+def colsum_(dy, db, N=None):
+    """db (f32) += column sums of dy (M, N) bf16."""
+    M = dy.shape[0]
+    N = dy.shape[1] if N is None else N
+    call("oasr_colsum_bf16", ptr(dy), ptr(db), M, N, dy.stride(0), stream())
+    return db
