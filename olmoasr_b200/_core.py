@@ -1,0 +1,672 @@
+"""Shared implementation behind olmoasr_b200.model (training model) and olmoasr_b200.inf_model (inference model).
+
+The module tree, parameter names / shapes and initialisation follow the reference exactly
+(olmoasr/model.py:14-968, olmoasr/inf_model.py) so that `state_dict()`s are interchangeable and DDP / FSDP /
+AdamW / checkpoint code written for the reference keeps working.  Every tensor operation is a call into
+liboasr_b200.so; computation is bf16 with fp32 master weights and fp32 statistics, i.e. the numerics of the
+reference under `torch.autocast("cuda", torch.bfloat16)` (scripts/training/train_timestamps.py:1414) with
+its rounding points reproduced (Linear outputs, GELU, residual adds, LayerNorm casts, bf16 logits).
+
+Training fast path: one autograd.Function per ResidualAttentionBlock (+ stem, embedding and loss head) whose
+backward is a hand-sequenced list of kernels -- dgrad / wgrad GEMMs read the saved activations through
+MN-major UMMA descriptors, so nothing is transposed in HBM.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Iterable, Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import Tensor, nn
+
+from . import kernels as K
+from .config.model_dims import ModelDimensions
+
+PAD_ID_EN = 51864  # padding token / padding_idx of the English-only vocabulary (model.py:665-667)
+
+
+# =====================================================================================================
+# small helpers
+# =====================================================================================================
+def _sm_count() -> int:
+    from ._lib import lib
+    return lib().oasr_device_sm_count()
+
+
+def _pick_block_n(M: int, N: int) -> int:
+    """Tile width for the persistent GEMM: fewest waves x tile cost; ties go to the wider tile."""
+    if N <= 64:
+        return 64
+    sms = _sm_count()
+    best, best_cost = 256, None
+    for bn in (256, 128):
+        tiles = math.ceil(M / 128) * math.ceil(N / bn)
+        cost = math.ceil(tiles / sms) * bn
+        if best_cost is None or cost < best_cost:
+            best, best_cost = bn, cost
+    return best
+
+
+def _pick_split_k(tiles: int, kblocks: int) -> int:
+    sms = _sm_count()
+    best, best_cost = 1, None
+    for s in range(1, 9):
+        if s > kblocks:
+            break
+        cost = math.ceil(tiles * s / sms) * (1.0 / s + 0.03)
+        if best_cost is None or cost < best_cost - 1e-9:
+            best, best_cost = s, cost
+    return best
+
+
+def linear_fwd(x: Tensor, w_bf16: Tensor, bias: Optional[Tensor], *, epi=K.EPI_BF16, aux=None, out=None):
+    """y = epi(x W^T + b): x (M, K) bf16, w (N, K) bf16 shadow of the fp32 master, bias (N,) f32."""
+    M, Kd = x.shape
+    N = w_bf16.shape[0]
+    return K.gemm(x, w_bf16, M, N, Kd, bias=bias, aux=aux, epi=epi, out=out, block_n=_pick_block_n(M, N))
+
+
+def linear_dgrad(dy: Tensor, w_bf16: Tensor, *, epi=K.EPI_BF16, aux=None, out=None):
+    """dx = dy W: dy (M, N) bf16, w (N, K) bf16 read MN-major."""
+    M, N = dy.shape
+    Kd = w_bf16.shape[1]
+    return K.gemm(dy, w_bf16, M, Kd, N, b_mn=True, epi=epi, aux=aux, out=out, block_n=_pick_block_n(M, Kd))
+
+
+def linear_wgrad(dy: Tensor, x: Tensor, n_valid: Optional[int] = None):
+    """dW (N, K) f32 = dy^T x.  Both operands are read MN-major straight from their (M, *) row-major storage
+    (A = dy^T is "stored (K=M, M=N)", B = x is "stored (K=M, N=K)"); split-K + fp32 red.add when the output has
+    too few tiles to fill the GPU."""
+    M = dy.shape[0]
+    N = dy.shape[1] if n_valid is None else n_valid
+    Kd = x.shape[1]
+    bn = 256 if Kd >= 256 else (128 if Kd > 64 else 64)
+    tiles = math.ceil(N / 128) * math.ceil(Kd / bn)
+    split = _pick_split_k(tiles, math.ceil(M / 64))
+    dyv = dy if n_valid is None else dy[:, :n_valid]
+    out = None if split == 1 else torch.zeros((N, Kd), device=x.device, dtype=torch.float32)
+    return K.gemm(dyv, x, N, Kd, M, a_mn=True, b_mn=True, out=out,
+                  epi=K.EPI_F32 if out is None else K.EPI_F32_ATOMIC_ADD, split_k=split, block_n=bn)
+
+
+def bias_grad(dy: Tensor, n: Optional[int] = None) -> Tensor:
+    n = dy.shape[1] if n is None else n
+    db = torch.zeros(n, device=dy.device, dtype=torch.float32)
+    return K.colsum_(dy, db, n)
+
+
+def kv_len_from_padding_mask(padding_mask: Tensor) -> Tensor:
+    """The reference passes a dense additive mask (B, 448, 448) whose columns >= len(text_input) are -inf for every
+    row (scripts/training/train_timestamps.py:314-315).  The kernels take that as a per-sample key count."""
+    return (padding_mask[:, 0, :] == 0).sum(dim=-1).to(torch.int32)
+
+
+class _ShadowCache:
+    """bf16 copies of fp32 master weights (+ fused biases), rebuilt only when a master changed."""
+
+    def __init__(self):
+        self.key = None
+        self.val = None
+
+    def get(self, params: Iterable[Tensor], build):
+        key = tuple((p.data_ptr(), p._version, p.device) for p in params)
+        if key != self.key:
+            with torch.no_grad():
+                self.val = build()
+            self.key = key
+        return self.val
+
+
+# =====================================================================================================
+# leaf modules (parameters live here, names identical to the reference)
+# =====================================================================================================
+class LayerNorm(nn.LayerNorm):
+    """olmoasr/model.py:14-39."""
+
+    def forward(self, x: Tensor) -> Tensor:
+        shp = x.shape
+        y = K.layernorm_fwd(_as_bf16_2d(x), self.weight, self.bias, self.eps, want_stats=False)
+        return y.view(shp)
+
+
+class Linear(nn.Linear):
+    """olmoasr/model.py:42-101: kaiming-normal weight, bf16 compute with the fp32 master cast on the fly."""
+
+    def __init__(self, in_features: int, out_features: int, bias: bool = True, device=None, dtype=None):
+        super().__init__(in_features, out_features, bias=bias, device=device, dtype=dtype)
+        nn.init.kaiming_normal_(self.weight, mode="fan_in", nonlinearity="relu")
+        self._shadow = _ShadowCache()
+
+    def weight_bf16(self) -> Tensor:
+        return self._shadow.get((self.weight,), lambda: K.cast_bf16(self.weight.detach().contiguous()))
+
+    def forward(self, x: Tensor) -> Tensor:  # inference / hook path (no autograd through the kernels)
+        shp = x.shape
+        y = linear_fwd(_as_bf16_2d(x), self.weight_bf16(), self.bias)
+        return y.view(*shp[:-1], self.out_features)
+
+
+class Conv1d(nn.Conv1d):
+    """olmoasr/model.py:104-195 (parameters only; the stem kernels are driven by AudioEncoder)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
+                 padding_mode="zeros", device=None, dtype=None):
+        super().__init__(in_channels, out_channels, kernel_size, stride=stride, padding=padding, dilation=dilation,
+                         groups=groups, bias=bias, padding_mode=padding_mode, device=device, dtype=dtype)
+        nn.init.kaiming_normal_(self.weight, mode="fan_in", nonlinearity="relu")
+        self._shadow = _ShadowCache()
+
+    def weight_bf16(self) -> Tensor:  # (C_out, 3*C_in) with column = k*C_in + c
+        return self._shadow.get((self.weight,), lambda: K.cast_conv_weight(self.weight.detach().contiguous()))
+
+
+def sinusoids(length, channels, max_timescale=10000):
+    """olmoasr/model.py:199-230."""
+    assert channels % 2 == 0
+    log_timescale_increment = np.log(max_timescale) / (channels // 2 - 1)
+    inv_timescales = torch.exp(-log_timescale_increment * torch.arange(channels // 2))
+    scaled_time = torch.arange(length)[:, np.newaxis] * inv_timescales[np.newaxis, :]
+    return torch.cat([torch.sin(scaled_time), torch.cos(scaled_time)], dim=1)
+
+
+def _as_bf16_2d(x: Tensor) -> Tensor:
+    if x.dtype != torch.bfloat16:
+        x = x.to(torch.bfloat16)
+    return x.reshape(-1, x.shape[-1]).contiguous()
+
+
+class MultiHeadAttention(nn.Module):
+    """olmoasr/model.py:233-442.  `double_init` reproduces the training model's second kaiming draw (model.py:258-264)
+    so that seeds give the reference's weights; the inference model draws once (inf_model.py:131-138)."""
+
+    def __init__(self, n_state: int, n_head: int, double_init: bool = True):
+        super().__init__()
+        self.n_head = n_head
+        self.query = Linear(n_state, n_state)
+        if double_init:
+            nn.init.kaiming_normal_(self.query.weight, mode="fan_in", nonlinearity="relu")
+        self.key = Linear(n_state, n_state, bias=False)
+        if double_init:
+            nn.init.kaiming_normal_(self.key.weight, mode="fan_in", nonlinearity="relu")
+        self.value = Linear(n_state, n_state)
+        if double_init:
+            nn.init.kaiming_normal_(self.value.weight, mode="fan_in", nonlinearity="relu")
+        self.out = Linear(n_state, n_state)
+        if double_init:
+            nn.init.kaiming_normal_(self.out.weight, mode="fan_in", nonlinearity="relu")
+        self._fused = _ShadowCache()
+
+    # ---- fused bf16 shadows -------------------------------------------------------------------------
+    def fused_qkv(self):
+        """([Wq;Wk;Wv] (3d, d) bf16, [bq;0;bv] (3d,) f32) -- key has no bias (model.py:259)."""
+        ps = (self.query.weight, self.key.weight, self.value.weight, self.query.bias, self.value.bias)
+
+        def build():
+            d = self.query.weight.shape[0]
+            w = torch.empty((3 * d, d), device=ps[0].device, dtype=torch.bfloat16)
+            for i, p in enumerate(ps[:3]):
+                K.cast_bf16(p.detach().contiguous(), w[i * d:(i + 1) * d])
+            b = torch.cat([ps[3].detach().float(), torch.zeros(d, device=ps[0].device), ps[4].detach().float()])
+            return w, b
+
+        return self._fused.get(ps, build)
+
+    def fused_kv(self):
+        w, b = self.fused_qkv()
+        d = self.query.weight.shape[0]
+        return w[d:], b[d:]
+
+    # ---- generic (hook-compatible) path: used for decoding with a kv cache --------------------------------
+    def forward(self, x: Tensor, xa: Optional[Tensor] = None, mask: Optional[Tensor] = None,
+                kv_cache: Optional[dict] = None, verbose: bool = False):
+        B, Tq, d = x.shape
+        q = self.query(x)
+        if kv_cache is None or xa is None or self.key not in kv_cache:
+            k = self.key(x if xa is None else xa)      # forward hooks (install_kv_cache_hooks) may swap these for the cache
+            v = self.value(x if xa is None else xa)
+        else:
+            k = kv_cache[self.key]
+            v = kv_cache[self.value]
+        Tkv = k.shape[1]
+        causal = mask is not None and xa is None and Tq == Tkv and Tq > 1
+        kv_len = None
+        if mask is not None and mask.dim() == 3:
+            kv_len = kv_len_from_padding_mask(mask)
+        o, _ = K.attention_fwd(q.reshape(B * Tq, d), k.reshape(B * Tkv, d), v.reshape(B * Tkv, d), B, self.n_head, Tq, Tkv,
+                               causal=causal, kv_len=kv_len, want_lse=False)
+        return self.out(o.view(B, Tq, d)), None
+
+
+# =====================================================================================================
+# fused training blocks
+# =====================================================================================================
+class _BlockFn(torch.autograd.Function):
+    """ResidualAttentionBlock.forward (model.py:485-528) for a (B*T, d) bf16 residual stream.
+
+    inputs: x, xa (or None), kv_len (or None), then the block's parameters in `ResidualAttentionBlock._param_list`
+    order.  Saves every GEMM input it needs for wgrad; recomputes nothing."""
+
+    @staticmethod
+    def forward(ctx, blk, B, T, Ta, causal, kv_len, x, xa, *params):
+        H = blk.attn.n_head
+        d = x.shape[1]
+        sh = blk._shadows()
+        ln1, mean1, rstd1 = K.layernorm_fwd(x, blk.attn_ln.weight, blk.attn_ln.bias)
+        qkv = linear_fwd(ln1, sh["wqkv"], sh["bqkv"])
+        ao, lse = K.attention_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], B, H, T, T, causal=causal, kv_len=kv_len)
+        x1 = linear_fwd(ao, sh["wo"], blk.attn.out.bias, epi=K.EPI_BF16_RESIDUAL, aux=x)
+        saved = [x, mean1, rstd1, ln1, qkv, ao, lse, x1]
+        if xa is not None:
+            lnc, meanc, rstdc = K.layernorm_fwd(x1, blk.cross_attn_ln.weight, blk.cross_attn_ln.bias)
+            qc = linear_fwd(lnc, sh["wcq"], blk.cross_attn.query.bias)
+            kvc = linear_fwd(xa, sh["wckv"], sh["bckv"])
+            co, lsec = K.attention_fwd(qc, kvc[:, :d], kvc[:, d:], B, H, T, Ta)
+            x2 = linear_fwd(co, sh["wco"], blk.cross_attn.out.bias, epi=K.EPI_BF16_RESIDUAL, aux=x1)
+            saved += [xa, meanc, rstdc, lnc, qc, kvc, co, lsec, x2]
+        else:
+            x2 = x1
+        ln2, mean2, rstd2 = K.layernorm_fwd(x2, blk.mlp_ln.weight, blk.mlp_ln.bias)
+        h, g = linear_fwd(ln2, sh["w1"], blk.mlp[0].bias, epi=K.EPI_BF16_GELU)
+        x3 = linear_fwd(g, sh["w2"], blk.mlp[2].bias, epi=K.EPI_BF16_RESIDUAL, aux=x2)
+        saved += [mean2, rstd2, ln2, h, g]
+        if kv_len is not None:
+            saved.append(kv_len)
+        ctx.save_for_backward(*saved)
+        ctx.blk, ctx.dims, ctx.sh = blk, (B, T, Ta, H, d, causal, xa is not None, kv_len is not None), sh
+        return x3
+
+    @staticmethod
+    def backward(ctx, dx3):
+        blk, sh = ctx.blk, ctx.sh
+        B, T, Ta, H, d, causal, cross, has_len = ctx.dims
+        sv = list(ctx.saved_tensors)
+        kv_len = sv.pop() if has_len else None
+        x, mean1, rstd1, ln1, qkv, ao, lse, x1 = sv[:8]
+        if cross:
+            xa, meanc, rstdc, lnc, qc, kvc, co, lsec, x2 = sv[8:17]
+            mean2, rstd2, ln2, h, g = sv[17:22]
+        else:
+            x2 = x1
+            mean2, rstd2, ln2, h, g = sv[8:13]
+        dx3 = dx3.contiguous()
+        dev = x.device
+        grads: Dict[str, Tensor] = {}
+        z = lambda n: torch.zeros(n, device=dev, dtype=torch.float32)
+
+        # ---- MLP: x3 = x2 + fc2(gelu(fc1(ln(x2))))
+        grads["mlp.2.weight"] = linear_wgrad(dx3, g)
+        grads["mlp.2.bias"] = bias_grad(dx3)
+        dh = linear_dgrad(dx3, sh["w2"], epi=K.EPI_BF16_GELU_BWD, aux=h)
+        grads["mlp.0.weight"] = linear_wgrad(dh, ln2)
+        grads["mlp.0.bias"] = bias_grad(dh)
+        dln2 = linear_dgrad(dh, sh["w1"])
+        grads["mlp_ln.weight"], grads["mlp_ln.bias"] = z(d), z(d)
+        dx2 = K.layernorm_bwd(dln2, x2, blk.mlp_ln.weight, mean2, rstd2, grads["mlp_ln.weight"], grads["mlp_ln.bias"],
+                              dresidual=dx3)
+        dxa = None
+        if cross:
+            # ---- cross attention: x2 = x1 + out(attn(q(ln(x1)), kv(xa)))
+            grads["cross_attn.out.weight"] = linear_wgrad(dx2, co)
+            grads["cross_attn.out.bias"] = bias_grad(dx2)
+            dco = linear_dgrad(dx2, sh["wco"])
+            dqc = torch.empty_like(qc)
+            dkvc = torch.empty_like(kvc)
+            K.attention_bwd(qc, kvc[:, :d], kvc[:, d:], co, dco, lsec, B, H, T, Ta, dq=dqc, dk=dkvc[:, :d], dv=dkvc[:, d:])
+            grads["cross_attn.query.weight"] = linear_wgrad(dqc, lnc)
+            grads["cross_attn.query.bias"] = bias_grad(dqc)
+            dwkv = linear_wgrad(dkvc, xa)
+            grads["cross_attn.key.weight"], grads["cross_attn.value.weight"] = dwkv[:d], dwkv[d:]
+            grads["cross_attn.value.bias"] = bias_grad(dkvc)[d:]
+            dxa = linear_dgrad(dkvc, sh["wckv"])
+            dlnc = linear_dgrad(dqc, sh["wcq"])
+            grads["cross_attn_ln.weight"], grads["cross_attn_ln.bias"] = z(d), z(d)
+            dx1 = K.layernorm_bwd(dlnc, x1, blk.cross_attn_ln.weight, meanc, rstdc, grads["cross_attn_ln.weight"],
+                                  grads["cross_attn_ln.bias"], dresidual=dx2)
+        else:
+            dx1 = dx2
+        # ---- self attention: x1 = x + out(attn(qkv(ln(x))))
+        grads["attn.out.weight"] = linear_wgrad(dx1, ao)
+        grads["attn.out.bias"] = bias_grad(dx1)
+        dao = linear_dgrad(dx1, sh["wo"])
+        dqkv = torch.empty_like(qkv)
+        K.attention_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], ao, dao, lse, B, H, T, T, causal=causal, kv_len=kv_len,
+                        dq=dqkv[:, :d], dk=dqkv[:, d:2 * d], dv=dqkv[:, 2 * d:])
+        dw = linear_wgrad(dqkv, ln1)
+        grads["attn.query.weight"], grads["attn.key.weight"], grads["attn.value.weight"] = dw[:d], dw[d:2 * d], dw[2 * d:]
+        db = bias_grad(dqkv)
+        grads["attn.query.bias"], grads["attn.value.bias"] = db[:d], db[2 * d:]
+        dln1 = linear_dgrad(dqkv, sh["wqkv"])
+        grads["attn_ln.weight"], grads["attn_ln.bias"] = z(d), z(d)
+        dx = K.layernorm_bwd(dln1, x, blk.attn_ln.weight, mean1, rstd1, grads["attn_ln.weight"], grads["attn_ln.bias"],
+                             dresidual=dx1)
+        return (None, None, None, None, None, None, dx, dxa, *[grads[n] for n in blk._param_names])
+
+
+class ResidualAttentionBlock(nn.Module):
+    """olmoasr/model.py:445-528 (the FSDP wrap / activation-checkpoint unit of train_fsdp_timestamps.py:2665-2719)."""
+
+    def __init__(self, n_state: int, n_head: int, cross_attention: bool = False, double_init: bool = True):
+        super().__init__()
+        self.attn = MultiHeadAttention(n_state, n_head, double_init)
+        self.attn_ln = LayerNorm(n_state)
+        self.cross_attn = MultiHeadAttention(n_state, n_head, double_init) if cross_attention else None
+        self.cross_attn_ln = LayerNorm(n_state) if cross_attention else None
+        n_mlp = n_state * 4
+        self.mlp = nn.Sequential(Linear(n_state, n_mlp), nn.GELU(), Linear(n_mlp, n_state))
+        self.mlp_ln = LayerNorm(n_state)
+        self._param_names = [n for n, _ in self.named_parameters()]
+        self._shadow = _ShadowCache()
+
+    def _shadows(self):
+        params = [p for _, p in self.named_parameters()]
+
+        def build():
+            sh = {}
+            sh["wqkv"], sh["bqkv"] = self.attn.fused_qkv()
+            sh["wo"] = self.attn.out.weight_bf16()
+            if self.cross_attn is not None:
+                sh["wcq"] = self.cross_attn.query.weight_bf16()
+                sh["wckv"], sh["bckv"] = self.cross_attn.fused_kv()
+                sh["wco"] = self.cross_attn.out.weight_bf16()
+            sh["w1"] = self.mlp[0].weight_bf16()
+            sh["w2"] = self.mlp[2].weight_bf16()
+            return sh
+
+        return self._shadow.get(params, build)
+
+    def forward(self, x: Tensor, xa: Optional[Tensor] = None, mask: Optional[Tensor] = None,
+                kv_cache: Optional[dict] = None, verbose: bool = False):
+        if kv_cache is not None:
+            return self._forward_cached(x, xa, mask, kv_cache)
+        B, T, d = x.shape
+        causal, kv_len = False, None
+        if mask is not None:
+            causal = True
+            if mask.dim() == 3:
+                kv_len = kv_len_from_padding_mask(mask)
+        Ta = xa.shape[1] if xa is not None else 0
+        xa2 = _as_bf16_2d(xa) if xa is not None else None
+        params = [self.get_parameter(n) for n in self._param_names]
+        y = _BlockFn.apply(self, B, T, Ta, causal, kv_len, _as_bf16_2d(x), xa2, *params)
+        return y.view(B, T, d)
+
+    def _forward_cached(self, x, xa, mask, kv_cache):
+        """Decode path: unfused modules so that the forward hooks on key / value fire (model.py:925-964)."""
+        B, T, d = x.shape
+        x = x + self.attn(self.attn_ln(x), mask=mask, kv_cache=kv_cache)[0]
+        if self.cross_attn is not None:
+            x = x + self.cross_attn(self.cross_attn_ln(x), xa, kv_cache=kv_cache)[0]
+        h, g = linear_fwd(_as_bf16_2d(self.mlp_ln(x)), self.mlp[0].weight_bf16(), self.mlp[0].bias, epi=K.EPI_BF16_GELU)
+        y = linear_fwd(g, self.mlp[2].weight_bf16(), self.mlp[2].bias, epi=K.EPI_BF16_RESIDUAL, aux=_as_bf16_2d(x))
+        return y.view(B, T, d)
+
+
+# =====================================================================================================
+# encoder
+# =====================================================================================================
+class _StemFn(torch.autograd.Function):
+    """conv1 -> GELU -> conv2 (stride 2) -> GELU -> transpose -> + sinusoids (model.py:592-602) as
+    im2col + tcgen05 GEMM with fused bias/GELU epilogues, time-major throughout."""
+
+    @staticmethod
+    def forward(ctx, enc, mel, w1, b1, w2, b2):
+        B, C, T = mel.shape
+        d = w1.shape[0]
+        T2 = (T + 2 - 3) // 2 + 1
+        A1 = K.im2col_conv1(mel.contiguous().float(), 3 * C)
+        pre1, h1 = linear_fwd(A1, enc.conv1.weight_bf16(), b1, epi=K.EPI_BF16_GELU)
+        A2 = K.im2col_conv2(h1, B, T, d)
+        pre2, h2 = linear_fwd(A2, enc.conv2.weight_bf16(), b2, epi=K.EPI_BF16_GELU)
+        x0 = K.add_pos(h2, enc.positional_embedding, T2)
+        ctx.save_for_backward(A1, pre1, A2, pre2)
+        ctx.enc, ctx.dims = enc, (B, C, T, T2, d)
+        return x0
+
+    @staticmethod
+    def backward(ctx, dx0):
+        A1, pre1, A2, pre2 = ctx.saved_tensors
+        enc = ctx.enc
+        B, C, T, T2, d = ctx.dims
+        dpre2 = K.gelu_bwd(dx0.contiguous(), pre2)
+        dw2 = K.unpermute_conv_wgrad(linear_wgrad(dpre2, A2), d, d)
+        db2 = bias_grad(dpre2)
+        dA2 = linear_dgrad(dpre2, enc.conv2.weight_bf16())
+        dpre1 = K.col2im_conv2_gelu_bwd(dA2, pre1, B, T, T2, d)
+        dw1 = K.unpermute_conv_wgrad(linear_wgrad(dpre1, A1), d, C)
+        db1 = bias_grad(dpre1)
+        return None, None, dw1, db1, dw2, db2
+
+
+class AudioEncoder(nn.Module):
+    """olmoasr/model.py:531-623."""
+
+    def __init__(self, n_mels: int, n_ctx: int, n_state: int, n_head: int, n_layer: int, double_init: bool = True):
+        super().__init__()
+        self.conv1 = Conv1d(n_mels, n_state, kernel_size=3, padding=1)
+        self.conv2 = Conv1d(n_state, n_state, kernel_size=3, stride=2, padding=1)
+        self.register_buffer("positional_embedding", sinusoids(n_ctx, n_state))
+        self.blocks: Iterable[ResidualAttentionBlock] = nn.ModuleList(
+            [ResidualAttentionBlock(n_state, n_head, double_init=double_init) for _ in range(n_layer)])
+        self.ln_post = LayerNorm(n_state)
+
+    def forward(self, x: Tensor, verbose: bool = False):
+        B = x.shape[0]
+        n_ctx, d = self.positional_embedding.shape
+        assert x.dim() == 3 and (x.shape[2] + 2 - 3) // 2 + 1 == n_ctx and x.shape[1] == self.conv1.in_channels, \
+            "incorrect audio shape"
+        x0 = _StemFn.apply(self, x, self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias)
+        h = x0.view(B, n_ctx, d)
+        for block in self.blocks:
+            h = block(h)
+        return _LayerNormFn.apply(h.reshape(B * n_ctx, d), self.ln_post.weight, self.ln_post.bias, self.ln_post.eps).view(B, n_ctx, d)
+
+
+class _LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        y, mean, rstd = K.layernorm_fwd(x, w, b, eps)
+        ctx.save_for_backward(x, w, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, mean, rstd = ctx.saved_tensors
+        dw = torch.zeros_like(w)
+        db = torch.zeros_like(w)
+        dx = K.layernorm_bwd(dy.contiguous(), x, w, mean, rstd, dw, db)
+        return dx, dw, db, None
+
+
+# =====================================================================================================
+# decoder
+# =====================================================================================================
+class _EmbedFn(torch.autograd.Function):
+    """(token_embedding(ids) + positional_embedding[offset:offset+S]).to(bf16)  (model.py:728-732)."""
+
+    @staticmethod
+    def forward(ctx, ids, emb, pos, offset, padding_idx):
+        out = K.embed_fwd(ids.contiguous(), emb, pos, offset)
+        ctx.save_for_backward(ids)
+        ctx.meta = (emb.shape, pos.shape, offset, padding_idx)
+        return out
+
+    @staticmethod
+    def backward(ctx, dx):
+        (ids,) = ctx.saved_tensors
+        eshape, pshape, offset, padding_idx = ctx.meta
+        demb = torch.zeros(eshape, device=dx.device, dtype=torch.float32)
+        dpos = torch.zeros(pshape, device=dx.device, dtype=torch.float32)
+        K.embed_bwd(ids.contiguous(), dx.contiguous(), demb, dpos[offset:], -1 if padding_idx is None else padding_idx)
+        return None, demb, dpos, None, None
+
+
+def _logits_ld(V: int) -> int:
+    return (V + 255) // 256 * 256  # 51865 -> 51968: no ragged tile in the logits GEMM, 16-byte aligned rows
+
+
+class _LogitsFn(torch.autograd.Function):
+    """(x @ token_embedding.weight.to(x.dtype).T).float()  (model.py:768-770) for callers that want logits."""
+
+    @staticmethod
+    def forward(ctx, x, emb, emb_bf16):
+        M, d = x.shape
+        V = emb.shape[0]
+        buf = torch.empty((M, _logits_ld(V)), device=x.device, dtype=torch.bfloat16)
+        K.gemm(x, emb_bf16, M, V, d, out=buf, block_n=256)
+        ctx.save_for_backward(x, emb_bf16)
+        return K.logits_to_f32(buf, V)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        x, emb_bf16 = ctx.saved_tensors
+        M, d = x.shape
+        V = emb_bf16.shape[0]
+        buf = torch.empty((M, _logits_ld(V)), device=x.device, dtype=torch.bfloat16)
+        buf[:, :V].copy_(dlogits)  # `.float()` backward: the gradient enters the matmul as bf16
+        dx = K.gemm(buf[:, :V], emb_bf16, M, d, V, b_mn=True, block_n=_pick_block_n(M, d))
+        demb = linear_wgrad(buf, x, n_valid=V)
+        return dx, demb, None
+
+
+class _LossHeadFn(torch.autograd.Function):
+    """Fused tail of the training step: tied logits GEMM (bf16, never widened to fp32) + token cross-entropy
+    (model.py:768-770 followed by train_timestamps.py:1444-1448).  The backward turns the logits buffer into
+    d(logits) in place and feeds it to the dgrad / wgrad GEMMs."""
+
+    @staticmethod
+    def forward(ctx, x, emb, emb_bf16, targets, ignore_index):
+        M, d = x.shape
+        V = emb.shape[0]
+        buf = torch.empty((M, _logits_ld(V)), device=x.device, dtype=torch.bfloat16)
+        K.gemm(x, emb_bf16, M, V, d, out=buf, block_n=256)
+        t = targets.reshape(-1).contiguous()
+        lse, lsc = K.ce_fwd(buf, t, V, ignore_index)
+        ctx.save_for_backward(x, emb_bf16, buf, t, lse, lsc)
+        ctx.meta = (V, ignore_index)
+        return lsc[0] / lsc[1]
+
+    @staticmethod
+    def backward(ctx, dloss):
+        x, emb_bf16, buf, t, lse, lsc = ctx.saved_tensors
+        V, ignore_index = ctx.meta
+        M, d = x.shape
+        K.ce_bwd_(buf, t, lse, lsc, dloss.reshape(1).float().contiguous(), V, ignore_index)
+        dx = K.gemm(buf[:, :V], emb_bf16, M, d, V, b_mn=True, block_n=_pick_block_n(M, d))
+        demb = linear_wgrad(buf, x, n_valid=V)
+        return dx, demb, None, None, None
+
+
+class TextDecoder(nn.Module):
+    """olmoasr/model.py:626-775 (train_vocab_pad=True: n_vocab+1 rows with padding_idx) and
+    olmoasr/inf_model.py:284-362 (train_vocab_pad=False)."""
+
+    def __init__(self, n_vocab: int, n_ctx: int, n_state: int, n_head: int, n_layer: int, train_vocab_pad: bool = True):
+        super().__init__()
+        if train_vocab_pad:
+            self.token_embedding = nn.Embedding(n_vocab + 1, n_state, padding_idx=51864 if n_vocab == 51864 else 51865)
+        else:
+            self.token_embedding = nn.Embedding(n_vocab, n_state)
+        nn.init.kaiming_normal_(self.token_embedding.weight, mode="fan_in", nonlinearity="relu")
+        self.positional_embedding = nn.Parameter(torch.empty(n_ctx, n_state))
+        if train_vocab_pad:
+            nn.init.kaiming_normal_(self.positional_embedding, mode="fan_in", nonlinearity="relu")
+        self.blocks: Iterable[ResidualAttentionBlock] = nn.ModuleList(
+            [ResidualAttentionBlock(n_state, n_head, cross_attention=True, double_init=train_vocab_pad) for _ in range(n_layer)])
+        self.ln = LayerNorm(n_state)
+        mask = torch.empty(n_ctx, n_ctx).fill_(-np.inf).triu_(1)
+        self.register_buffer("mask", mask, persistent=False)
+        self._emb_shadow = _ShadowCache()
+
+    def embedding_bf16(self) -> Tensor:
+        w = self.token_embedding.weight
+        return self._emb_shadow.get((w,), lambda: K.cast_bf16(w.detach().contiguous()))
+
+    def hidden(self, x: Tensor, xa: Tensor, kv_cache: Optional[dict] = None, padding_mask: Optional[Tensor] = None) -> Tensor:
+        """Everything up to and including the final LayerNorm: (B, S) ids -> (B*S, d) bf16."""
+        offset = next(iter(kv_cache.values())).shape[1] if kv_cache else 0
+        B, S = x.shape
+        d = self.positional_embedding.shape[1]
+        h = _EmbedFn.apply(x, self.token_embedding.weight, self.positional_embedding, offset,
+                           self.token_embedding.padding_idx).view(B, S, d)
+        mask = padding_mask if padding_mask is not None else self.mask[:S, :S]
+        for block in self.blocks:
+            h = block(h, xa, mask=mask, kv_cache=kv_cache)
+        return _LayerNormFn.apply(h.reshape(B * S, d), self.ln.weight, self.ln.bias, self.ln.eps)
+
+    def forward(self, x: Tensor, xa: Tensor, kv_cache: Optional[dict] = None, padding_mask: Optional[Tensor] = None,
+                verbose: bool = False):
+        B, S = x.shape
+        h = self.hidden(x, xa, kv_cache, padding_mask)
+        logits = _LogitsFn.apply(h, self.token_embedding.weight, self.embedding_bf16())
+        return logits.view(B, S, -1)
+
+    def loss(self, x: Tensor, xa: Tensor, targets: Tensor, padding_mask: Optional[Tensor] = None, ignore_index: int = PAD_ID_EN):
+        h = self.hidden(x, xa, None, padding_mask)
+        return _LossHeadFn.apply(h, self.token_embedding.weight, self.embedding_bf16(), targets, ignore_index)
+
+
+# =====================================================================================================
+# top-level model
+# =====================================================================================================
+class OLMoASRBase(nn.Module):
+    """olmoasr/model.py:778-968 / olmoasr/inf_model.py:365-457."""
+
+    _train_vocab_pad = True
+
+    def __init__(self, dims: ModelDimensions):
+        super().__init__()
+        self.dims = dims
+        tv = self._train_vocab_pad
+        self.encoder = AudioEncoder(dims.n_mels, dims.n_audio_ctx, dims.n_audio_state, dims.n_audio_head,
+                                    dims.n_audio_layer, double_init=tv)
+        self.decoder = TextDecoder(dims.n_vocab, dims.n_text_ctx, dims.n_text_state, dims.n_text_head,
+                                   dims.n_text_layer, train_vocab_pad=tv)
+
+    def embed_audio(self, mel: Tensor):
+        return self.encoder(mel)
+
+    def logits(self, tokens: Tensor, audio_features: Tensor, padding_mask: Tensor = None):
+        return self.decoder(tokens, audio_features, padding_mask=padding_mask)
+
+    def forward(self, mel: Tensor, tokens: Tensor, padding_mask: Tensor = None, verbose: bool = False) -> Tensor:
+        return self.decoder(tokens, self.encoder(mel), padding_mask=padding_mask)
+
+    def loss(self, mel: Tensor, tokens: Tensor, targets: Tensor, padding_mask: Tensor = None, ignore_index: int = PAD_ID_EN):
+        """Fused equivalent of `F.cross_entropy(model(mel, tokens, padding_mask).view(-1, V), targets.view(-1),
+        ignore_index=51864)` (train_timestamps.py:1440-1448) that never materialises fp32 logits."""
+        return self.decoder.loss(tokens, self.encoder(mel), targets, padding_mask, ignore_index)
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    @property
+    def is_multilingual(self):
+        return self.dims.n_vocab >= 51865
+
+    @property
+    def num_languages(self):
+        return self.dims.n_vocab - 51765 - int(self.is_multilingual)
+
+    def install_kv_cache_hooks(self, cache: Optional[dict] = None):
+        """Same contract as the reference (model.py:925-964): forward hooks on every decoder key / value Linear,
+        keyed by module identity; outputs longer than n_text_ctx (cross-attention) are stored once."""
+        cache = {**cache} if cache is not None else {}
+        hooks = []
+
+        def save_to_cache(module, _, output):
+            if module not in cache or output.shape[1] > self.dims.n_text_ctx:
+                cache[module] = output
+            else:
+                cache[module] = torch.cat([cache[module], output], dim=1).detach()
+            return cache[module]
+
+        def install_hooks(layer: nn.Module):
+            if isinstance(layer, MultiHeadAttention):
+                hooks.append(layer.key.register_forward_hook(save_to_cache))
+                hooks.append(layer.value.register_forward_hook(save_to_cache))
+
+        self.decoder.apply(install_hooks)
+        return cache, hooks

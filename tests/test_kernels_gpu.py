@@ -196,7 +196,7 @@ def test_conv_stem_pieces(K):
     ref2 = F.conv1d(h1.float().view(B, T, d).permute(0, 2, 1), w2.bfloat16().float(), b2.bfloat16().float(), stride=2, padding=1)
     _close(pre2.view(B, 1500, d), ref2.permute(0, 2, 1))
     pos = torch.randn(1500, d, device="cuda")
-    _close(K.add_pos(h2, pos, 1500), h2.float().view(B, 1500, d) + pos)
+    _close(K.add_pos(h2, pos, 1500).view(B, 1500, d), h2.float().view(B, 1500, d) + pos)
     # col2im + gelu backward against autograd of conv2 w.r.t. its input
     dA = torch.randn(B * 1500, 3 * d, device="cuda").bfloat16()
     hin = torch.zeros(B, d, T, device="cuda", requires_grad=True)
