@@ -143,6 +143,17 @@ OASR_API int oasr_add_pos(const void* x, const float* pos, void* out, int64_t ro
 OASR_API int oasr_gelu_bwd(const void* dy, const void* pre, void* out, int64_t n, void* stream);
 OASR_API int oasr_colsum_bf16(const void* dy, float* db, int64_t M, int64_t N, int64_t ld, void* stream);
 
+/* ---- fused optimizer step ("next" row: scripts/training/train_timestamps.py:1508-1522) -----------------
+ * recs: device table of {float* p, const float* g, float* m, float* v, int64 numel} per tensor; chunks: device
+ * int2 {tensor index, chunk index} with oasr_optim_chunk_elems() elements per chunk.  grad_sqnorm writes the sum
+ * of squares of all gradients to out[0]; adamw_step applies unscale (inv_scale), clip_grad_norm_(max_norm) and the
+ * AdamW update, and leaves everything untouched (found_inf[0] = 1) when the norm is not finite. */
+OASR_API int oasr_optim_chunk_elems(void);
+OASR_API int oasr_grad_sqnorm(const void* recs, const void* chunks, int64_t n_chunks, float* out, void* stream);
+OASR_API int oasr_adamw_step(const void* recs, const void* chunks, int64_t n_chunks, const float* norm_sq,
+                             float* found_inf, float inv_scale, float max_norm, float lr, float beta1, float beta2,
+                             float eps, float weight_decay, int64_t step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

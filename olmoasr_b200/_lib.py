@@ -52,6 +52,10 @@ _SIGNATURES = {
     "oasr_add_pos": [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p],
     "oasr_gelu_bwd": [c_void_p, c_void_p, c_void_p, c_i64, c_void_p],
     "oasr_colsum_bf16": [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p],
+    "oasr_optim_chunk_elems": [],
+    "oasr_grad_sqnorm": [c_void_p, c_void_p, c_i64, c_void_p, c_void_p],
+    "oasr_adamw_step": [c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_float,
+                        c_float, c_float, c_i64, c_void_p],
     "oasr_gemm_bf16": [c_void_p, c_i64, c_int, c_void_p, c_i64, c_int, c_void_p, c_i64, c_void_p, c_void_p,
                        c_void_p, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_void_p],
 }

@@ -61,7 +61,7 @@ def test_forward_logits_and_loss(setup, golden_dir):
     assert _rel(got[:, ::16, ::997], g["logits_bf16_sample"]) <= 1e-2
 
 
-def test_fused_loss_and_gradients(setup):
+def test_fused_loss_and_gradients(setup, golden_dir):
     s = setup
     OM, m = s["OM"], s["m"]
     p = {k: v.clone().requires_grad_(k != "encoder.positional_embedding") for k, v in s["sd"].items()}
@@ -78,8 +78,12 @@ def test_fused_loss_and_gradients(setup):
         worst.append((r, k))
     worst.sort(reverse=True)
     print("largest gradient rel-L2 errors:", [(f"{r:.3e}", k) for r, k in worst[:6]])
-    assert worst[0][0] <= 6e-2, worst[:4]          # every tensor
-    assert sum(r for r, _ in worst) / len(worst) <= 2e-2
+    # yardstick: the reference's OWN bf16-autocast gradients against its fp32 gradients (tools/make_golden.py);
+    # e.g. cross-attention query weights carry ~11 % bf16 noise at initialisation in the reference itself
+    noise = torch.load(golden_dir / "grad_noise_tiny.pt", weights_only=False)
+    for r, k in worst:
+        assert r <= max(1.5 * noise[k], 2e-2), (k, r, noise[k])
+    assert sum(r for r, _ in worst) / len(worst) <= 1.5 * sum(noise.values()) / len(noise)
     assert m.decoder.token_embedding.weight.grad[51864].abs().max().item() <= 1e-6 + m.decoder.token_embedding.weight.grad.abs().max().item()
     # drop-in path (fp32 logits + F.cross_entropy + autograd) gives the same gradients as the fused head
     g_fused = {k: q.grad.clone() for k, q in m.named_parameters()}

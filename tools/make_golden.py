@@ -106,6 +106,26 @@ def golden_model():
     print("inf_tiny.pt")
 
 
+def golden_grad_noise():
+    """Per-tensor relative L2 distance between the reference's bf16-autocast gradients and its fp32 gradients
+    (tiny, seed 0, the synthetic batch): the yardstick for gradient parity of any bf16 implementation."""
+    dims = OM.variant_dims("tiny")
+    sd = OM.init_state_dict(dims, 0, True)  # bit-identical to the reference's weights (tests/test_oracle_pin.py)
+    B = 2
+    mel = torch.from_numpy(logmel.log_mel_spectrogram(synth.waveforms(B).numpy()))
+    ti, ty, pm, _ = synth.text_batch(B)
+
+    def grads(ac):
+        p = {k: v.clone().requires_grad_(k != "encoder.positional_embedding") for k, v in sd.items()}
+        OM.token_ce(OM.model_forward(p, dims, mel, ti, pm, True, ac), ty).backward()
+        return {k: v.grad for k, v in p.items() if v.grad is not None}
+
+    g32, gbf = grads(None), grads(torch.bfloat16)
+    torch.save({k: float((gbf[k] - g32[k]).norm() / g32[k].norm()) for k in g32}, OUT / "grad_noise_tiny.pt")
+    print("grad_noise_tiny.pt")
+
+
 if __name__ == "__main__":
     golden_logmel()
     golden_model()
+    golden_grad_noise()
