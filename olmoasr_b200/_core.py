@@ -630,7 +630,12 @@ class OLMoASRBase(nn.Module):
     def logits(self, tokens: Tensor, audio_features: Tensor, padding_mask: Tensor = None):
         return self.decoder(tokens, audio_features, padding_mask=padding_mask)
 
-    def forward(self, mel: Tensor, tokens: Tensor, padding_mask: Tensor = None, verbose: bool = False) -> Tensor:
+    def forward(self, mel: Tensor, tokens: Tensor, padding_mask: Tensor = None, verbose: bool = False, *,
+                targets: Optional[Tensor] = None, ignore_index: int = PAD_ID_EN) -> Tensor:
+        """Reference signature (model.py:856-887) -> fp32 logits.  With the keyword-only `targets` the call returns
+        the token cross-entropy instead (fused head); going through forward() keeps DDP / FSDP wrappers in the loop."""
+        if targets is not None:
+            return self.decoder.loss(tokens, self.encoder(mel), targets, padding_mask, ignore_index)
         return self.decoder(tokens, self.encoder(mel), padding_mask=padding_mask)
 
     def loss(self, mel: Tensor, tokens: Tensor, targets: Tensor, padding_mask: Tensor = None, ignore_index: int = PAD_ID_EN):

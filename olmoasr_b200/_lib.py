@@ -108,6 +108,13 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# kernels launched per entry point (memsets not counted) -- bench.py reports the total as `gpu_launches`
+_LAUNCHES_PER_CALL = {"oasr_logmel": 3, "oasr_attention_bwd": 3}
+LAUNCH_COUNT = 0
+
+
 def call(name: str, *args):
+    global LAUNCH_COUNT
     fn = getattr(lib(), name)
     check(fn(*args), name)
+    LAUNCH_COUNT += _LAUNCHES_PER_CALL.get(name, 1)

@@ -13,7 +13,7 @@ from .config.model_dims import ModelDimensions
 class OLMoASR(OLMoASRBase):
     _train_vocab_pad = False
 
-    def forward(self, mel: Tensor, tokens: Tensor, padding_mask: Optional[Tensor] = None) -> Tensor:
+    def forward(self, mel: Tensor, tokens: Tensor, padding_mask: Optional[Tensor] = None) -> Tensor:  # inf_model.py:403-406
         return self.decoder(tokens, self.encoder(mel), padding_mask=padding_mask)
 
     def decode(self, mel, options=None, **kwargs):

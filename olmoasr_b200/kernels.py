@@ -14,6 +14,11 @@ K_MAJOR, MN_MAJOR = 0, 1
 EPI_BF16, EPI_BF16_GELU, EPI_BF16_RESIDUAL, EPI_BF16_GELU_BWD, EPI_F32, EPI_F32_ATOMIC_ADD = range(6)
 
 
+# When set to a list, every GEMM launch is bracketed by CUDA events on the launching stream and
+# (flops, start, end) is appended: bench.py derives the tensor-pipe roofline figure of the dominant kernel from it.
+GEMM_PROFILE = None
+
+
 def _req(cond, msg):
     if not cond:
         raise ValueError(msg)
@@ -40,9 +45,17 @@ def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, out=None, out2=None, bias=Non
         _req(aux.dtype == torch.bfloat16 and aux.stride(1) == 1 and aux.shape[0] == M, "gemm: aux")
     if bias is not None:
         _req(bias.dtype == torch.float32 and bias.numel() >= N and bias.is_contiguous(), "gemm: bias must be f32")
+    prof = GEMM_PROFILE
+    if prof is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
     call("oasr_gemm_bf16", ptr(a), a.stride(0), int(a_mn), ptr(b), b.stride(0), int(b_mn),
          ptr(out), out.stride(0), ptr(out2), ptr(bias), ptr(aux), aux.stride(0) if aux is not None else 0,
          M, N, K, epi, split_k, block_n, stream())
+    if prof is not None:
+        e1.record()
+        prof.append((2.0 * M * N * K, e0, e1))
     if epi == EPI_BF16_GELU:
         return out, out2
     return out
