@@ -148,7 +148,7 @@ def our_arm(args):
     from olmoasr_b200 import kernels as K
     from olmoasr_b200.model import OLMoASR
     from olmoasr_b200.optim import FusedAdamW
-    from oracle import synth  # input generator only (pure tensor construction, no model code)
+    from olmoasr_b200 import synthetic as synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

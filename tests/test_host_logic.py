@@ -1,0 +1,161 @@
+"""Host-side logic that needs no GPU: module tree / state-dict contract, initial weights, tile heuristics, audio
+helpers, synthetic batch, checkpoint loading, and the data-parallel semantics on a 2-rank gloo group."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import olmoasr_b200 as ob
+from olmoasr_b200 import _core, audio, synthetic
+from oracle import logmel
+from oracle import model as OM
+
+
+def test_state_dict_contract_and_initial_weights_match_reference():
+    for train in (True, False):
+        torch.manual_seed(0)
+        m = (ob.model.OLMoASR if train else ob.inf_model.OLMoASR)(ob.VARIANT_TO_DIMS["tiny"])
+        sd = OM.init_state_dict(OM.variant_dims("tiny"), seed=0, train=train)   # pinned to the reference in test_oracle_pin
+        msd = m.state_dict()
+        assert set(msd) == set(sd)
+        for k in sd:
+            assert msd[k].shape == sd[k].shape, k
+            if train or k != "decoder.positional_embedding":   # inf_model leaves it uninitialised (inf_model.py:307)
+                assert torch.equal(msd[k], sd[k]), k
+        assert "decoder.mask" not in msd and m.decoder.mask.shape == (448, 448)   # non-persistent buffer
+        assert m.decoder.token_embedding.weight.shape[0] == (51865 if train else 51864)
+        assert m.is_multilingual is False and m.num_languages == 99
+    from olmoasr_b200.model import ResidualAttentionBlock  # FSDP wrap unit must be importable (train_fsdp_timestamps.py:59-61)
+    assert isinstance(m.encoder.blocks[0], ResidualAttentionBlock)
+
+
+def test_parameter_counts():
+    want = {"tiny": 37.18e6, "base": 71.83e6}   # SURVEY.md section 0 (train model incl. the pad row)
+    for name, n in want.items():
+        with torch.device("meta"):
+            m = ob.model.OLMoASR(ob.VARIANT_TO_DIMS[name])
+        got = sum(p.numel() for p in m.parameters())
+        assert abs(got - n) / n < 2e-3, (name, got)
+
+
+def test_tile_heuristics():
+    _core._sm_count = lambda: 148
+    assert _core._pick_block_n(48000, 1024) in (128, 256)
+    assert _core._pick_block_n(100, 64) == 64
+    for tiles, kb in ((32, 750), (128, 750), (1624, 224), (1, 1)):
+        s = _core._pick_split_k(tiles, kb)
+        assert 1 <= s <= min(8, kb)
+    assert _core._pick_split_k(32, 750) > 1          # 32 output tiles cannot fill 148 SMs without split-K
+    assert _core._pick_split_k(1624, 224) == 1
+
+
+def test_kv_len_from_padding_mask():
+    _, _, pm, lens = synthetic.text_batch(5)
+    assert torch.equal(_core.kv_len_from_padding_mask(pm).long(), lens)
+
+
+def test_audio_helpers_match_oracle():
+    assert np.array_equal(audio.mel_filterbank(80), logmel.mel_filters(80))
+    x = np.arange(10, dtype=np.float32)
+    assert np.array_equal(audio.pad_or_trim(x, 4), logmel.pad_or_trim(x, 4))
+    assert np.array_equal(audio.pad_or_trim(x, 12), logmel.pad_or_trim(x, 12))
+    t = torch.arange(10.0)
+    assert audio.pad_or_trim(t, 12).shape == (12,) and audio.pad_or_trim(t, 3).tolist() == [0.0, 1.0, 2.0]
+    assert (audio.N_SAMPLES, audio.N_FRAMES, audio.HOP_LENGTH, audio.N_FFT) == (480000, 3000, 160, 400)
+    if not torch.cuda.is_available():
+        from olmoasr_b200._lib import OasrError
+        with pytest.raises(OasrError):   # no silent CPU fallback
+            audio.log_mel_spectrogram(np.zeros(480000, np.float32))
+
+
+def test_synthetic_batch_follows_the_dataset_contract():
+    ti, ty, pm, lens = synthetic.text_batch(4)
+    assert ti.shape == ty.shape == (4, 448) and pm.shape == (4, 448, 448)
+    for i in range(4):
+        n = int(lens[i])
+        assert n == 32 + (37 * i) % 192 - 1
+        assert ti[i, 0] == 50257 and ti[i, 1] == 50362 and ty[i, n - 1] == 50256
+        assert (ti[i, n:] == 51864).all() and (ty[i, n:] == 51864).all()
+        assert torch.equal(ti[i, 1:n], ty[i, : n - 1])
+        assert (pm[i, :, :n] == 0).all() and torch.isinf(pm[i, :, n:]).all()
+    w = synthetic.waveforms(2, int16=True)
+    assert w.dtype == torch.int16 and w.shape == (2, 480000)
+
+
+def test_load_model_reads_reference_checkpoints(tmp_path):
+    torch.manual_seed(1)
+    dims = ob.VARIANT_TO_DIMS["tiny"]
+    m = ob.model.OLMoASR(dims)
+    # the reference's DDP checkpoint layout: "module."-prefixed keys, dims as the dataclass (train_timestamps.py:930-955)
+    ck = {"dims": dims, "model_state_dict": {"module." + k: v for k, v in m.state_dict().items()}}
+    f = tmp_path / "ddp.pt"
+    torch.save(ck, f)
+    m2 = ob.load_model(str(f), device="cpu")
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+    # inference checkpoint: pad row dropped, dims as a dict (scripts/eval/gen_inf_ckpt.py:4-11)
+    sd = dict(m.state_dict())
+    sd["decoder.token_embedding.weight"] = sd["decoder.token_embedding.weight"][:-1]
+    f2 = tmp_path / "inf.pt"
+    torch.save({"dims": dict(vars(dims)), "model_state_dict": sd}, f2)
+    m3 = ob.load_model(str(f2), device="cpu", inference=True, in_memory=True)
+    assert m3.decoder.token_embedding.weight.shape[0] == 51864
+    with pytest.raises(ValueError):
+        ob.load_model("no-such-model", device="cpu")
+
+
+# ---------------------------------------------------------------------------------------------- 2-rank gloo
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _ddp_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # per-rank shard of the synthetic batch (seeded by rank, as bench.py does) and DDP's mean-of-per-rank-means loss
+    ti, ty, pm, lens = synthetic.text_batch(3, rank=rank)
+    torch.manual_seed(0)
+    w = torch.nn.Linear(8, 4)
+    ddp = torch.nn.parallel.DistributedDataParallel(w)
+    x = torch.randn(5, 8, generator=torch.Generator().manual_seed(100 + rank))
+    loss = ddp(x).pow(2).mean()          # per-rank mean, like F.cross_entropy over this rank's tokens
+    loss.backward()
+    g = w.weight.grad.clone()
+    gathered = [torch.zeros_like(g) for _ in range(world)]
+    dist.all_gather(gathered, g)
+    t = torch.tensor([float(rank + 1) * 10.0])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)   # bench.py: max-over-ranks step time
+    if rank == 0:
+        torch.save({"grads": gathered, "lens": lens, "tmax": float(t)}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_semantics_world2_gloo(tmp_path):
+    out = str(tmp_path / "r0.pt")
+    port = _free_port()
+    mp.spawn(_ddp_worker, args=(2, port, out), nprocs=2, join=True)
+    r = torch.load(out, weights_only=False)
+    assert torch.allclose(r["grads"][0], r["grads"][1])           # gradients are averaged across ranks
+    assert r["tmax"] == 20.0
+    # ranks draw different shards
+    a = synthetic.text_batch(3, rank=0)[0]
+    b = synthetic.text_batch(3, rank=1)[0]
+    assert not torch.equal(a, b)
+    # reference arithmetic: grad of mean-of-per-rank-means == average of per-rank grads
+    torch.manual_seed(0)
+    w = torch.nn.Linear(8, 4)
+    gs = []
+    for rank in range(2):
+        w.zero_grad()
+        x = torch.randn(5, 8, generator=torch.Generator().manual_seed(100 + rank))
+        w(x).pow(2).mean().backward()
+        gs.append(w.weight.grad.clone())
+    assert torch.allclose(r["grads"][0], (gs[0] + gs[1]) / 2, atol=1e-6)
