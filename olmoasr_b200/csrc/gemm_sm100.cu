@@ -3,11 +3,15 @@
 //
 //   D[M,N] = epi( sum_k A[m,k] B[n,k] )
 //
-// One CTA per SM, 256 threads:
-//   warp 0      TMA producer (one lane)
-//   warp 1      MMA issuer   (one lane)
-//   warp 2      TMEM allocator / deallocator
-//   warps 4..7  epilogue: each owns TMEM lanes 32*(warp%4) .. +31 (one output row per thread)
+// One CTA per SM, 384 threads:
+//   warp 0       TMA producer (one lane)
+//   warp 1       MMA issuer   (one lane)
+//   warp 2       TMEM allocator / deallocator
+//   warps 4..11  epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 (one output row per thread) and the column
+//                half (w-4)/4 of the tile
+// CLUSTER = 2: two CTAs that share an N tile (consecutive M tiles) form a cluster; each loads half of the B tile and
+// TMA-multicasts it to both, which halves the L2 -> SM operand traffic of B (the 128 x 256 tile is otherwise
+// L2-bandwidth bound: 85 FLOP/B against ~12 TB/s).  Stage release is a multicast tcgen05.commit to both CTAs.
 //
 // Tile = 128 x BN, BK = 64 bf16 (= one 128-byte swizzle row).  Both operand majors are supported
 // through the UMMA descriptors, so dgrad (B MN-major) and wgrad (A and B MN-major) need no
@@ -15,6 +19,8 @@
 // autograd, model.py:768-770 (tied logits), model.py:592-593 (Conv1d after im2col).
 #include "common.cuh"
 #include "ptx_sm100.cuh"
+
+#include <stdlib.h>
 
 namespace oasr {
 namespace {
@@ -81,8 +87,8 @@ __device__ __forceinline__ void load_bf16x32(const bf16* src, float (&x)[32], in
   }
 }
 
-template <int BN, int A_MN, int B_MN>
-__global__ void __launch_bounds__(256, 1)
+template <int BN, int A_MN, int B_MN, int CLUSTER>
+__global__ void __launch_bounds__(384, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmParams p) {
   using C = Cfg<BN>;
@@ -94,6 +100,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __shared__ __align__(8) uint64_t bar_tmem_full[2];
   __shared__ __align__(8) uint64_t bar_tmem_empty[2];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float s_bias[2][BN];
 
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5;
@@ -106,11 +113,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bar_full[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bar_empty[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bar_empty[s]), CLUSTER);  // every CTA of the cluster releases the slot
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bar_tmem_full[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bar_tmem_empty[s]), 4);  // one arrive per epilogue warp
+      ptx::mbar_init(ptx::smem_u32(&bar_tmem_empty[s]), 8);  // one arrive per epilogue warp
     }
     ptx::fence_barrier_init();
   }
@@ -120,20 +127,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CLUSTER > 1) ptx::cluster_sync();  // peer barriers are initialised before any multicast / remote arrive
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
-  const int num_tiles = p.tiles_m * p.tiles_n * p.splits;
+  // tile walk: with CLUSTER = 2 the pair (2*pm, 2*pm+1) of M tiles shares n_blk; both CTAs see the same sequence
+  const uint32_t cta_rank = (CLUSTER > 1) ? ptx::cluster_ctarank() : 0;
+  const int tiles_mc = (p.tiles_m + CLUSTER - 1) / CLUSTER;
+  const int num_tiles = tiles_mc * p.tiles_n * p.splits;
+  const int tile0 = blockIdx.x / CLUSTER;
+  const int tile_step = gridDim.x / CLUSTER;
+  constexpr uint16_t kMask = (1u << CLUSTER) - 1;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int n_blk = tile % p.tiles_n;
-        const int m_blk = (tile / p.tiles_n) % p.tiles_m;
-        const int split = tile / (p.tiles_n * p.tiles_m);
+        const int m_blk = ((tile / p.tiles_n) % tiles_mc) * CLUSTER + cta_rank;
+        const int split = tile / (p.tiles_n * tiles_mc);
         const int kb0 = split * p.kblocks_per_split;
         const int kb1 = min(kb0 + p.kblocks_per_split, p.kblocks_total);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -149,12 +163,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           } else {
             ptx::tma_load_2d(sa, &tmA, full, kb * BK, m_blk * BM);
           }
-          if (B_MN) {
+          if (CLUSTER == 1) {
+            if (B_MN) {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i)
-              ptx::tma_load_2d(sb + i * (BK * 128), &tmB, full, n_blk * BN + i * 64, kb * BK);
+              for (int i = 0; i < BN / 64; ++i)
+                ptx::tma_load_2d(sb + i * (BK * 128), &tmB, full, n_blk * BN + i * 64, kb * BK);
+            } else {
+              ptx::tma_load_2d(sb, &tmB, full, kb * BK, n_blk * BN);
+            }
           } else {
-            ptx::tma_load_2d(sb, &tmB, full, kb * BK, n_blk * BN);
+            // this CTA fetches half of the B tile and multicasts it into both CTAs' stage buffers
+            if (B_MN) {
+#pragma unroll
+              for (int i = 0; i < BN / 128; ++i) {
+                const int c = cta_rank * (BN / 128) + i;  // 64-column chunk index
+                ptx::tma_load_2d_mc(sb + c * (BK * 128), &tmB, full, n_blk * BN + c * 64, kb * BK, kMask);
+              }
+            } else {
+              const int r0 = cta_rank * (BN / 2);
+              ptx::tma_load_2d_mc(sb + r0 * 128, &tmB, full, kb * BK, n_blk * BN + r0, kMask);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -174,8 +202,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int split = tile / (p.tiles_n * p.tiles_m);
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        const int split = tile / (p.tiles_n * tiles_mc);
         const int kb0 = split * p.kblocks_per_split;
         const int kb1 = min(kb0 + p.kblocks_per_split, p.kblocks_total);
         ptx::mbar_wait(ptx::smem_u32(&bar_tmem_empty[acc]), acc_phase ^ 1);
@@ -192,7 +220,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint64_t bd = ptx::umma_smem_desc_sw128(sb + k * b_kstep, b_lbo, b_sbo);
             ptx::tc_mma_f16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          ptx::tc_commit(ptx::smem_u32(&bar_empty[stage]));  // frees the smem slot when MMAs retire
+          // frees the smem slot (in every CTA that multicasts into it) when the MMAs retire
+          if (CLUSTER == 1) ptx::tc_commit(ptx::smem_u32(&bar_empty[stage]));
+          else ptx::tc_commit_mc(ptx::smem_u32(&bar_empty[stage]), kMask);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         ptx::tc_commit(ptx::smem_u32(&bar_tmem_full[acc]));  // accumulator complete
@@ -202,22 +232,32 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int q = warp & 3;            // TMEM lane quarter this warp may touch
+    const int chalf = (warp - 4) >> 2; // which half of the tile's columns this warp drains
+    const int etid = threadIdx.x - 128;
     const int row_in_tile = q * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool c_is_f32 = (p.epi == OASR_EPI_F32 || p.epi == OASR_EPI_F32_ATOMIC_ADD);
     const bool vec_c = c_is_f32 ? ((p.ldc & 3) == 0) : ((p.ldc & 7) == 0);
     const bool vec_aux = (p.ldaux & 7) == 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int n_blk = tile % p.tiles_n;
-      const int m_blk = (tile / p.tiles_n) % p.tiles_m;
+      const int m_blk = ((tile / p.tiles_n) % tiles_mc) * CLUSTER + cta_rank;
       const int row = m_blk * BM + row_in_tile;
       const bool row_ok = row < p.M;
+      if (p.bias != nullptr) {  // stage this tile's bias once (rounded to bf16 like bias.to(x.dtype) unless fp32 output)
+        for (int i = etid; i < BN; i += 256) {
+          const int col = n_blk * BN + i;
+          const float b = col < p.N ? __ldg(p.bias + col) : 0.f;
+          s_bias[acc][i] = c_is_f32 ? b : bf16_round(b);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // epilogue warps only
+      }
       ptx::mbar_wait(ptx::smem_u32(&bar_tmem_full[acc]), acc_phase);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
         uint32_t r[32];
         __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent `continue`
         ptx::tc_ld_32x32b_x32(t_row + c * 32, r);
@@ -229,14 +269,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]);
         if (p.bias != nullptr) {
-          if (c_is_f32) {
+          const float4* b4 = reinterpret_cast<const float4*>(&s_bias[acc][c * 32]);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < nvalid) x[j] += __ldg(p.bias + col + j);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < nvalid) x[j] += bf16_round(__ldg(p.bias + col + j));
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = b4[j];
+            x[4 * j] += b.x; x[4 * j + 1] += b.y; x[4 * j + 2] += b.z; x[4 * j + 3] += b.w;
           }
         }
         const int64_t off = static_cast<int64_t>(row) * p.ldc + col;
@@ -312,35 +349,48 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (CLUSTER > 1) ptx::cluster_sync();  // no CTA exits while its peer can still multicast into it
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<C::TMEM_COLS>(tmem_base);
   }
 }
 
-template <int BN, int A_MN, int B_MN>
+template <int BN, int A_MN, int B_MN, int CLUSTER>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
   using C = Cfg<BN>;
-  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, CLUSTER>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     OASR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  const int tiles = p.tiles_m * p.tiles_n * p.splits;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, 256, C::SMEM_BYTES, st>>>(tmA, tmB, p);
-  OASR_LAUNCH_CHECK();
+  const int tiles = ((p.tiles_m + CLUSTER - 1) / CLUSTER) * p.tiles_n * p.splits;  // cluster tiles
+  const int max_clusters = num_sms() / CLUSTER;
+  const int grid = (tiles < max_clusters ? tiles : max_clusters) * CLUSTER;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(384);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CLUSTER;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  OASR_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
   return OASR_OK;
 }
 
-template <int BN>
+template <int BN, int CLUSTER>
 int dispatch_major(int a_mn, int b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB,
                    const GemmParams& p, cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch<BN, 0, 0>(tmA, tmB, p, st);
-  if (!a_mn && b_mn) return launch<BN, 0, 1>(tmA, tmB, p, st);
-  if (a_mn && b_mn) return launch<BN, 1, 1>(tmA, tmB, p, st);
-  return launch<BN, 1, 0>(tmA, tmB, p, st);
+  if (!a_mn && !b_mn) return launch<BN, 0, 0, CLUSTER>(tmA, tmB, p, st);
+  if (!a_mn && b_mn) return launch<BN, 0, 1, CLUSTER>(tmA, tmB, p, st);
+  if (a_mn && b_mn) return launch<BN, 1, 1, CLUSTER>(tmA, tmB, p, st);
+  return launch<BN, 1, 0, CLUSTER>(tmA, tmB, p, st);
 }
 
 }  // namespace
@@ -386,16 +436,23 @@ extern "C" int oasr_gemm_bf16(const void* A, int64_t lda, int a_layout, const vo
   else
     rc = make_tmap_2d(&tmA, A, 2, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64, BK, true);
   if (rc) return rc;
-  if (b_layout == OASR_K_MAJOR)
-    rc = make_tmap_2d(&tmB, B, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BK, block_n, true);
+  static const int env_cluster0 = [] { const char* e = getenv("OASR_GEMM_CLUSTER"); return e ? atoi(e) : 2; }();
+  const bool pair0 = env_cluster0 >= 2 && p.tiles_m >= 2 && block_n >= 128;
+  if (b_layout == OASR_K_MAJOR)  // paired CTAs each fetch (and multicast) half of the B tile's rows
+    rc = make_tmap_2d(&tmB, B, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BK, pair0 ? block_n / 2 : block_n, true);
   else
     rc = make_tmap_2d(&tmB, B, 2, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, BK, true);
   if (rc) return rc;
 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // multicast pairs need >= 2 M tiles and a B tile that splits in two TMA boxes; OASR_GEMM_CLUSTER=1 disables (A/B tests)
+  static const int env_cluster = [] { const char* e = getenv("OASR_GEMM_CLUSTER"); return e ? atoi(e) : 2; }();
+  const bool pair = env_cluster >= 2 && p.tiles_m >= 2 && block_n >= 128;
   switch (block_n) {
-    case 256: return dispatch_major<256>(a_layout, b_layout, tmA, tmB, p, st);
-    case 128: return dispatch_major<128>(a_layout, b_layout, tmA, tmB, p, st);
-    default: return dispatch_major<64>(a_layout, b_layout, tmA, tmB, p, st);
+    case 256: return pair ? dispatch_major<256, 2>(a_layout, b_layout, tmA, tmB, p, st)
+                          : dispatch_major<256, 1>(a_layout, b_layout, tmA, tmB, p, st);
+    case 128: return pair ? dispatch_major<128, 2>(a_layout, b_layout, tmA, tmB, p, st)
+                          : dispatch_major<128, 1>(a_layout, b_layout, tmA, tmB, p, st);
+    default: return dispatch_major<64, 1>(a_layout, b_layout, tmA, tmB, p, st);
   }
 }

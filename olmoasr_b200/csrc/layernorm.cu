@@ -9,9 +9,9 @@
 namespace oasr {
 namespace {
 
-constexpr int LN_MAX_VEC = 5;  // d <= 5 * 32 * 8 = 1280
+constexpr int LN_MAX_VEC = 5;  // d <= 5 * 32 * 8 = 1280; kernels are instantiated per ceil(d / 256) to bound registers
 
-template <bool kWriteStats>
+template <bool kWriteStats, int NV>
 __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                      bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
@@ -22,10 +22,10 @@ layernorm_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w, co
   for (int64_t row = static_cast<int64_t>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); row < rows;
        row += static_cast<int64_t>(gridDim.x) * warps_per_block) {
     const uint4* xr = reinterpret_cast<const uint4*>(x + row * d);
-    float v[LN_MAX_VEC][8];
+    float v[NV][8];
     float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int vi = lane + 32 * i;
       if (vi < nvec) {
         const uint4 u = xr[vi];
@@ -39,7 +39,7 @@ layernorm_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w, co
     const float mean = warp_sum(sum) / d;
     float sq = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i)
+    for (int i = 0; i < NV; ++i)
       if (lane + 32 * i < nvec) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) { const float c = v[i][j] - mean; sq += c * c; }
@@ -48,7 +48,7 @@ layernorm_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w, co
     if (kWriteStats && lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
     uint4* yr = reinterpret_cast<uint4*>(y + row * d);
 #pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int vi = lane + 32 * i;
       if (vi < nvec) {
         const float4 w0 = __ldg(reinterpret_cast<const float4*>(w) + 2 * vi), w1 = __ldg(reinterpret_cast<const float4*>(w) + 2 * vi + 1);
@@ -69,6 +69,7 @@ layernorm_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w, co
 
 // One warp per row; per-lane dw/db partials live in registers across the rows a warp visits, are
 // combined across the block's warps in shared memory and flushed with one atomicAdd per column.
+template <int NV>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ w,
                      const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -78,9 +79,9 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nvec = d >> 3;
-  float aw[LN_MAX_VEC][8], ab[LN_MAX_VEC][8];
+  float aw[NV][8], ab[NV][8];
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i)
+  for (int i = 0; i < NV; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) { aw[i][j] = 0.f; ab[i][j] = 0.f; }
   for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) red[i] = 0.f;
@@ -91,10 +92,10 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
     const uint4* xr = reinterpret_cast<const uint4*>(x + row * d);
     const uint4* gr = reinterpret_cast<const uint4*>(dy + row * d);
     const float mu = mean[row], rs = rstd[row];
-    float xh[LN_MAX_VEC][8], g[LN_MAX_VEC][8];
+    float xh[NV][8], g[NV][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int vi = lane + 32 * i;
       if (vi < nvec) {
         const uint4 ux = xr[vi], ug = gr[vi];
@@ -120,7 +121,7 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
     uint4* dxr = reinterpret_cast<uint4*>(dx + row * d);
     const uint4* rr = dres ? reinterpret_cast<const uint4*>(dres + row * d) : nullptr;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int vi = lane + 32 * i;
       if (vi < nvec) {
         float o[8];
@@ -142,7 +143,7 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
   }
   // block-level reduction of the parameter gradients
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int vi = lane + 32 * i;
     if (vi < nvec) {
 #pragma unroll
@@ -174,10 +175,20 @@ extern "C" int oasr_layernorm_fwd(const void* x, const float* weight, const floa
   int64_t blocks = ceil_div(rows, wpb);
   const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
   if (blocks > cap) blocks = cap;
-  if (mean)
-    layernorm_fwd_kernel<true><<<(int)blocks, wpb * 32, 0, st>>>((const bf16*)x, weight, bias, (bf16*)y, mean, rstd, rows, (int)d, eps);
-  else
-    layernorm_fwd_kernel<false><<<(int)blocks, wpb * 32, 0, st>>>((const bf16*)x, weight, bias, (bf16*)y, nullptr, nullptr, rows, (int)d, eps);
+#define OASR_LN_FWD(NVv)                                                                                          \
+  do {                                                                                                           \
+    if (mean)                                                                                                    \
+      layernorm_fwd_kernel<true, NVv><<<(int)blocks, wpb * 32, 0, st>>>((const bf16*)x, weight, bias, (bf16*)y, mean, rstd, rows, (int)d, eps); \
+    else                                                                                                         \
+      layernorm_fwd_kernel<false, NVv><<<(int)blocks, wpb * 32, 0, st>>>((const bf16*)x, weight, bias, (bf16*)y, nullptr, nullptr, rows, (int)d, eps); \
+  } while (0)
+  switch ((int)ceil_div(d, 256)) {
+    case 1: case 2: OASR_LN_FWD(2); break;
+    case 3: OASR_LN_FWD(3); break;
+    case 4: OASR_LN_FWD(4); break;
+    default: OASR_LN_FWD(5); break;
+  }
+#undef OASR_LN_FWD
   OASR_LAUNCH_CHECK();
   return OASR_OK;
 }
@@ -192,8 +203,16 @@ extern "C" int oasr_layernorm_bwd(const void* dy, const void* x, const float* we
   int64_t blocks = ceil_div(rows, wpb);
   const int64_t cap = static_cast<int64_t>(num_sms()) * 4;  // few blocks => few global atomics, long register reuse
   if (blocks > cap) blocks = cap;
-  layernorm_bwd_kernel<<<(int)blocks, wpb * 32, 2 * d * sizeof(float), st>>>(
-      (const bf16*)dy, (const bf16*)x, weight, mean, rstd, (const bf16*)dresidual, (bf16*)dx, dweight, dbias, rows, (int)d);
+#define OASR_LN_BWD(NVv)                                                                      \
+  layernorm_bwd_kernel<NVv><<<(int)blocks, wpb * 32, 2 * d * sizeof(float), st>>>(           \
+      (const bf16*)dy, (const bf16*)x, weight, mean, rstd, (const bf16*)dresidual, (bf16*)dx, dweight, dbias, rows, (int)d)
+  switch ((int)ceil_div(d, 256)) {
+    case 1: case 2: OASR_LN_BWD(2); break;
+    case 3: OASR_LN_BWD(3); break;
+    case 4: OASR_LN_BWD(4); break;
+    default: OASR_LN_BWD(5); break;
+  }
+#undef OASR_LN_BWD
   OASR_LAUNCH_CHECK();
   return OASR_OK;
 }

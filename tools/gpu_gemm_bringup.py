@@ -127,6 +127,13 @@ def main():
     cfgs.append(dict(base, M=48000, N=1024, K=1024, bn=256, b_mn=1, time=1, name="perf dgrad"))
     cfgs.append(dict(base, M=1024, N=1024, K=48000, bn=256, a_mn=1, b_mn=1, epi=5, split=5, time=1, name="perf wgrad split5"))
     cfgs.append(dict(base, M=8192, N=8192, K=8192, bn=256, time=1, name="perf 8192^3"))
+    cfgs.append(dict(base, M=14336, N=1024, K=1024, bn=128, bias=1, time=1, name="perf dec proj bn128"))
+    cfgs.append(dict(base, M=14336, N=51865, K=1024, bn=256, time=1, name="perf logits"))
+    cfgs.append(dict(base, M=2048 + 128, N=1024, K=512, bn=256, name="odd number of M tiles (17)"))
+    cfgs.append(dict(base, M=2048 + 128, N=1024, K=512, bn=128, b_mn=1, name="odd M tiles, B MN-major"))
+    for c in list(cfgs):
+        if c.get("time"):
+            cfgs.append(dict(c, cluster=1, name=c["name"] + " [no multicast]"))
     only = sys.argv[1] if len(sys.argv) > 1 else None
     n_fail = 0
     for c in cfgs:
@@ -134,7 +141,11 @@ def main():
             continue
         t = time.time()
         try:
-            r = subprocess.run([sys.executable, __file__, "one", json.dumps(c)], capture_output=True, text=True, timeout=180)
+            import os
+            env = dict(os.environ)
+            if "cluster" in c:
+                env["OASR_GEMM_CLUSTER"] = str(c["cluster"])
+            r = subprocess.run([sys.executable, __file__, "one", json.dumps(c)], capture_output=True, text=True, timeout=180, env=env)
             res = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
             if r.returncode != 0 or not res:
                 n_fail += 1

@@ -1,0 +1,67 @@
+"""Per-kernel device-time breakdown of one training step (torch.profiler / CUPTI), for profiles/.
+
+    python tools/profile_step.py [--variant medium] [--batch 32] > gpurun_out/step_profile.txt
+"""
+import argparse
+import sys
+from collections import defaultdict
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--variant", default="medium")
+    ap.add_argument("--batch", type=int, default=32)
+    args = ap.parse_args()
+    import olmoasr_b200 as ob
+    from olmoasr_b200 import synthetic as synth
+    from olmoasr_b200.model import OLMoASR
+    from olmoasr_b200.optim import FusedAdamW
+
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    with torch.device(dev):
+        model = OLMoASR(ob.VARIANT_TO_DIMS[args.variant])
+    opt = FusedAdamW(model.parameters())
+    B = args.batch
+    wav = synth.waveforms(B, int16=True).to(dev)
+    ti, ty, pm, _ = (t.to(dev) for t in synth.text_batch(B))
+
+    def step():
+        mel = ob.log_mel_spectrogram(wav)
+        loss = model(mel, ti, pm, targets=ty)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    from torch.profiler import ProfilerActivity, profile
+
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        step()
+        torch.cuda.synchronize()
+    agg = defaultdict(lambda: [0.0, 0])
+    for ev in prof.events():
+        if ev.device_type == torch.autograd.DeviceType.CUDA:
+            name = ev.name
+            for key in ("gemm_tcgen05_kernel", "attention_fwd_kernel", "attention_bwd_kernel"):
+                if key in name:
+                    name = key + ("" if key != "gemm_tcgen05_kernel" else name[name.find("<"):name.find(">") + 1])
+            agg[name][0] += ev.device_time_total if hasattr(ev, "device_time_total") else ev.cuda_time_total
+            agg[name][1] += 1
+    total = sum(v[0] for v in agg.values())
+    print(f"# {args.variant} B={B}: one training step, sum of kernel device time {total / 1e3:.2f} ms")
+    print(f"{'kernel':90s} {'calls':>6s} {'ms':>9s} {'share':>7s}")
+    for name, (t, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+        print(f"{name[:90]:90s} {n:6d} {t / 1e3:9.3f} {100 * t / total:6.2f}%")
+
+
+if __name__ == "__main__":
+    main()
