@@ -41,9 +41,11 @@ def _pick_block_n(M: int, N: int) -> int:
         return 64
     sms = _sm_count()
     best, best_cost = 256, None
-    for bn in (256, 128):
+    # measured on B200 (profiles/r01_gemm_bringup2_cluster.log): the 128-wide tile runs at ~70 % of the 256-wide
+    # tile's rate (64 vs 85 FLOP per operand byte), so it only wins when it saves >= 30 % of the waves
+    for bn, penalty in ((256, 1.0), (128, 1.4)):
         tiles = math.ceil(M / 128) * math.ceil(N / bn)
-        cost = math.ceil(tiles / sms) * bn
+        cost = math.ceil(tiles / sms) * bn * penalty
         if best_cost is None or cost < best_cost:
             best, best_cost = bn, cost
     return best

@@ -283,19 +283,31 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
 }
 
-// delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]   (one warp per (row, head): 64 elements, 2 per lane)
+// delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]   (8 lanes per (row, head), 16-byte loads, 3 shuffle steps)
 __global__ void attention_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, float* __restrict__ delta,
                                        int64_t ldo, int64_t lddo, int B, int H, int Tq) {
-  const int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+  const int64_t item = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 3;  // (row, head) pair
+  const int sub = threadIdx.x & 7;
   const int64_t total = static_cast<int64_t>(B) * Tq * H;
-  if (w >= total) return;
-  const int h = w % H;
-  const int64_t row = w / H;  // b*Tq + q
-  const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(o + row * ldo + h * HD + lane * 2));
-  const float2 g = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dout + row * lddo + h * HD + lane * 2));
-  const float s = warp_sum(a.x * g.x + a.y * g.y);
-  if (lane == 0) {
+  float s = 0.f;
+  int h = 0;
+  int64_t row = 0;
+  if (item < total) {
+    h = item % H;
+    row = item / H;  // b*Tq + q
+    const uint4 a = *reinterpret_cast<const uint4*>(o + row * ldo + h * HD + sub * 8);
+    const uint4 g = *reinterpret_cast<const uint4*>(dout + row * lddo + h * HD + sub * 8);
+    const uint32_t av[4] = {a.x, a.y, a.z, a.w}, gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 p = unpack_bf16x2(av[j]), q = unpack_bf16x2(gv[j]);
+      s += p.x * q.x + p.y * q.y;
+    }
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  if (sub == 0 && item < total) {
     const int b = row / Tq, q = row % Tq;
     delta[(static_cast<int64_t>(b) * H + h) * Tq + q] = s;
   }
@@ -339,8 +351,8 @@ extern "C" int oasr_attention_bwd(const void* q, int64_t ldq, const void* k, int
   if ((rc = make_tmap_2d(&tmV, v, 2, (uint64_t)(H * HD), (uint64_t)(B * Tkv), (uint64_t)ldv * 2, HD, BKV, true))) return rc;
   if ((rc = make_tmap_2d(&tmdO, dout, 2, (uint64_t)(H * HD), (uint64_t)(B * Tq), (uint64_t)lddo * 2, HD, BQ, true))) return rc;
 
-  const int64_t n_warps = B * Tq * H;
-  attention_delta_kernel<<<(unsigned)ceil_div(n_warps * 32, 256), 256, 0, st>>>((const bf16*)o, (const bf16*)dout, delta, ldo, lddo,
+  const int64_t n_items = B * Tq * H;
+  attention_delta_kernel<<<(unsigned)ceil_div(n_items * 8, 256), 256, 0, st>>>((const bf16*)o, (const bf16*)dout, delta, ldo, lddo,
                                                                               (int)B, (int)H, (int)Tq);
   OASR_LAUNCH_CHECK();
   OASR_CUDA_OK(cudaMemsetAsync(dq_accum, 0, sizeof(float) * B * Tq * H * HD, st));

@@ -48,12 +48,25 @@ __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + 
 // ---- small device helpers ---------------------------------------------------------------
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
+// erf via Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7): ~12 instructions instead of erff's ~30.  The GELU
+// epilogue of the fc1 GEMM is otherwise issue-bound (128 x 256 erff per tile against 8192 cycles of MMA at K = 1024);
+// the error is 4 orders of magnitude below the bf16 rounding applied to the result.
+__device__ __forceinline__ float erf_fast(float x) {
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(t, p, 1.421413741f);
+  p = fmaf(t, p, -0.284496736f);
+  p = fmaf(t, p, 0.254829592f);
+  const float r = fmaf(-p * t, __expf(-ax * ax), 1.0f);
+  return copysignf(r, x);
+}
 __device__ __forceinline__ float gelu_erf(float x) {
   // nn.GELU() / F.gelu default: 0.5 x (1 + erf(x / sqrt(2)))   (reference olmoasr/model.py:480-482,592-593)
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752440f));
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float cdf = 0.5f * (1.0f + erf_fast(x * 0.70710678118654752440f));
   const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
   return cdf + x * pdf;
 }

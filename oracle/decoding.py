@@ -34,7 +34,9 @@ def greedy_decode(sd, dims: OM.Dims, mel: torch.Tensor, sample_len: Optional[int
                   without_timestamps: bool = True, return_margins: bool = False):
     """Returns the list of generated token-id lists (up to, not including, eot) for each clip."""
     assert without_timestamps, "the oracle restates the short-form eval configuration only"
-    sdc = {k: v.to(dtype) if v.is_floating_point() else v for k, v in sd.items()}
+    # DecodingTask feeds a half-precision mel into fp32 weights; Linear / Conv1d cast their weights per call
+    # (inf_model.py:56-60), LayerNorm stays fp32 -- so only the input is cast here
+    sdc = sd
     xa = OM.encoder_forward(sdc, dims, mel.to(dtype), sdpa=False)
     n = mel.shape[0]
     initial = [SOT, NO_TIMESTAMPS]
