@@ -11,6 +11,8 @@
 //                                                             the "transposes" are MN-major descriptors)
 // dV and dK stay resident in TMEM for the whole loop; dQ_i is drained per query tile and reduced across
 // key tiles with vectorised fp32 red.global.add into a scratch buffer (converted to bf16 afterwards).
+// 320 threads: TMA warp, MMA warp, 8 compute warps (two per TMEM lane quarter, each taking half of the 128 key
+// columns; packed FFMA2 / FADD2 / FMUL2 math).
 // TMEM map (512 cols): S 0..127 | dP 128..255 | dV 256..319 | dK 320..383 | dQ 384..447.
 #include "common.cuh"
 #include "ptx_sm100.cuh"
@@ -56,7 +58,7 @@ __device__ __forceinline__ void store_swizzled_row32(uint32_t tile_base, int r, 
   }
 }
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                      const BwdParams p) {
@@ -94,7 +96,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     ptx::tma_prefetch_desc(&tmQ); ptx::tma_prefetch_desc(&tmK); ptx::tma_prefetch_desc(&tmV); ptx::tma_prefetch_desc(&tmdO);
     ptx::mbar_init(ptx::smem_u32(&bar_kv), 1);
     ptx::mbar_init(ptx::smem_u32(&bar_sdp), 1);
-    ptx::mbar_init(ptx::smem_u32(&bar_pds), 4);
+    ptx::mbar_init(ptx::smem_u32(&bar_pds), 8);
     ptx::mbar_init(ptx::smem_u32(&bar_dq), 1);
     ptx::mbar_init(ptx::smem_u32(&bar_done), 1);
     for (int s = 0; s < 2; ++s) {
@@ -179,7 +181,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
   } else {
     // ----------------------------- compute warps -----------------------------
+    // 8 warps: warp w owns TMEM lanes 32*(w%4).. (query row r = key row r for dK/dV) and the column half (w-2)/4
     const int quarter = warp & 3;
+    const int chalf = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;
     const uint32_t t_lane = static_cast<uint32_t>(quarter * 32) << 16;
     const float c = p.scale_log2;
@@ -195,19 +199,27 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       if (!q_ok) limit = 0;
       ptx::mbar_wait(ptx::smem_u32(&bar_sdp), it & 1);
       ptx::tc_fence_after();
+      const float2 c2 = make_float2(c, c), nl2 = make_float2(-lse, -lse), nd2 = make_float2(-dlt, -dlt);
 #pragma unroll 1
-      for (int cc = 0; cc < BKV / 32; ++cc) {
+      for (int cc = chalf * 2; cc < chalf * 2 + 2; ++cc) {
         uint32_t sv[32], dv[32];
         ptx::tc_ld_32x32b_x32(tmem + t_lane + S_COL + cc * 32, sv);
         ptx::tc_ld_32x32b_x32(tmem + t_lane + DP_COL + cc * 32, dv);
         ptx::tc_wait_ld();
         float pr[32], ds[32];
+        const bool full = (cc + 1) * 32 <= limit;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const bool vis = cc * 32 + i < limit;
-          const float pv = vis ? fast_exp2(__uint_as_float(sv[i]) * c - lse) : 0.f;
-          pr[i] = pv;
-          ds[i] = pv * (__uint_as_float(dv[i]) - dlt);
+        for (int i = 0; i < 32; i += 2) {
+          const float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), c2, nl2);
+          float2 pe = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+          if (!full) {
+            if (cc * 32 + i >= limit) pe.x = 0.f;
+            if (cc * 32 + i + 1 >= limit) pe.y = 0.f;
+          }
+          const float2 dd = __fadd2_rn(make_float2(__uint_as_float(dv[i]), __uint_as_float(dv[i + 1])), nd2);
+          const float2 dsv = __fmul2_rn(pe, dd);
+          pr[i] = pe.x; pr[i + 1] = pe.y;
+          ds[i] = dsv.x; ds[i + 1] = dsv.y;
         }
         store_swizzled_row32(sP, r, cc, pr);
         store_swizzled_row32(sdS, r, cc, ds);
@@ -220,8 +232,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       ptx::mbar_wait(ptx::smem_u32(&bar_dq), it & 1);
       ptx::tc_fence_after();
       float* dq_row = p.dq_accum + (static_cast<int64_t>(b) * p.Tq + qi) * (p.H * HD) + h * HD;
-#pragma unroll
-      for (int cc = 0; cc < HD / 32; ++cc) {
+      {
+        const int cc = chalf;
         uint32_t v[32];
         ptx::tc_ld_32x32b_x32(tmem + t_lane + DQ_COL + cc * 32, v);
         ptx::tc_wait_ld();
@@ -245,8 +257,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
     bf16* dk_row = p.dk + (static_cast<int64_t>(b) * p.Tkv + ki) * p.lddk + h * HD;
     bf16* dv_row = p.dv + (static_cast<int64_t>(b) * p.Tkv + ki) * p.lddv + h * HD;
-#pragma unroll
-    for (int cc = 0; cc < HD / 32; ++cc) {
+    {
+      const int cc = chalf;
       uint32_t a[32], bq[32];
       if (n_iter > 0) {
         ptx::tc_ld_32x32b_x32(tmem + t_lane + DV_COL + cc * 32, a);
@@ -367,7 +379,7 @@ extern "C" int oasr_attention_bwd(const void* q, int64_t ldq, const void* k, int
     attr_set = true;
   }
   dim3 grid((unsigned)ceil_div(Tkv, BKV), (unsigned)H, (unsigned)B);
-  attention_bwd_kernel<<<grid, 192, BWD_SMEM, st>>>(tmQ, tmK, tmV, tmdO, p);
+  attention_bwd_kernel<<<grid, 320, BWD_SMEM, st>>>(tmQ, tmK, tmV, tmdO, p);
   OASR_LAUNCH_CHECK();
   const int64_t rows = B * Tq;
   int64_t blocks = ceil_div(rows * (H * HD / 8), 256);

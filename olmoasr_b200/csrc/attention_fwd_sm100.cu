@@ -6,12 +6,18 @@
 //   encoder self-attention (no mask), decoder self-attention (causal + per-sample key length, derived
 //   from the dense additive mask the reference passes, model.py:740-743) and cross-attention (no mask).
 //
-// CTA = 128 query rows x one (b, h); loops over 128-key tiles.  192 threads:
-//   warp 0      TMA producer (Q once, K/V double-buffered)      warp 1   tcgen05.mma issuer + TMEM owner
-//   warps 2..5  softmax: thread r owns score row r (TMEM lane r) -> no cross-thread reductions at all
-// TMEM: S (128 cols fp32) + PV (64 cols fp32) -> 256-column allocation, two CTAs per SM so one CTA's
-// softmax overlaps the other's MMAs.  P is written to smem as bf16 in the 128B-swizzled K-major layout
-// and fed back as the A operand of the P*V MMA; V is consumed MN-major straight from its TMA tile.
+// CTA = 256 query rows (two 128-row tiles) x one (b, h); loops over 128-key tiles.  320 threads:
+//   warp 0      TMA producer (Q once, K/V double-buffered; every K/V tile serves both query tiles)
+//   warp 1      tcgen05.mma issuer + TMEM owner; interleaves the two query tiles so that one tile's MMAs run
+//               while the other tile's softmax warps work
+//   warps 2..5  softmax warpgroup of query tile 0      warps 6..9  softmax warpgroup of query tile 1
+// Thread r of a warpgroup owns score row r (= TMEM lane r): the row maximum and sum need no shuffles.
+// TMEM (512 cols): S0 0..127 | S1 128..255 | O0 256..319 | O1 320..383.  O is accumulated by the P*V MMAs
+// directly in TMEM; it is rescaled (tcgen05.ld -> scale -> tcgen05.st) only when a row maximum grows by more
+// than 2^8 -- otherwise the stale maximum is kept (probabilities stay <= 256, exact in bf16/fp32 terms).
+// The score row is read from TMEM once and kept in registers; scale/subtract and the row sum use packed
+// FFMA2 / FADD2, the maximum FMNMX3.  P goes to smem as bf16 in the 128B-swizzled K-major layout and is the
+// A operand of the P*V MMA; V is consumed MN-major straight from its TMA tile.
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 
@@ -19,14 +25,15 @@ namespace oasr {
 namespace {
 
 constexpr int HD = 64;
-constexpr int BQ = 128;
+constexpr int BQ = 128;                      // rows per query tile (two tiles per CTA)
 constexpr int BKV = 128;
 constexpr int TILE_BYTES = 128 * HD * 2;     // 16 KB: a [128 rows][64 bf16] swizzled tile
 constexpr int P_BYTES = BQ * BKV * 2;        // 32 KB: two 64-key halves of [128][128B]
-constexpr int ATT_TILES = TILE_BYTES /*Q*/ + 2 * 2 * TILE_BYTES /*K,V x2*/ + P_BYTES;  // 112 KB
-constexpr int ATT_SMEM = ATT_TILES + 128;  // + barriers; 2 CTAs/SM => no static smem, no alignment slack
-constexpr int TMEM_COLS = 256;
-constexpr int S_COL = 0, PV_COL = 128;
+constexpr int ATT_TILES = 2 * TILE_BYTES /*Q0,Q1*/ + 2 * 2 * TILE_BYTES /*K,V x2*/ + 2 * P_BYTES;  // 160 KB
+constexpr int ATT_SMEM = ATT_TILES + 256;
+constexpr int TMEM_COLS = 512;
+constexpr int S_COL = 0, O_COL = 256;        // + t*128 / + t*64
+constexpr float RESCALE_LOG2 = 8.0f;
 
 struct AttnParams {
   bf16* o;
@@ -38,44 +45,50 @@ struct AttnParams {
   float scale_log2;  // scale * log2(e)
 };
 
-__global__ void __launch_bounds__(192, 2)
+__global__ void __maxnreg__(200)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + ATT_TILES);
   uint64_t& bar_q = bars[0];
-  uint64_t& bar_s = bars[1];
-  uint64_t& bar_p = bars[2];
-  uint64_t& bar_pv = bars[3];
-  uint64_t* bar_kv_full = bars + 4;
-  uint64_t* bar_kv_empty = bars + 6;
-  uint32_t& tmem_slot = *reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* bar_s = bars + 1;         // [2]
+  uint64_t* bar_p = bars + 3;         // [2]
+  uint64_t* bar_pv = bars + 5;        // [2]
+  uint64_t* bar_kv_full = bars + 7;   // [2]
+  uint64_t* bar_kv_empty = bars + 9;  // [2]
+  uint32_t& tmem_slot = *reinterpret_cast<uint32_t*>(bars + 11);
 
   const uint32_t sbase = ptx::smem_u32(smem_raw);
   if ((sbase & 1023u) != 0) {  // swizzled tiles need 1 KB alignment; the declaration above should guarantee it
     if (threadIdx.x == 0) printf("oasr attention: dynamic smem base %u not 1 KB aligned\n", sbase);
     __trap();
   }
-  const uint32_t sQ = sbase;
-  const uint32_t sK0 = sQ + TILE_BYTES;              // stage s: K at sK0 + s*32K, V right after K
-  const uint32_t sP = sK0 + 4 * TILE_BYTES;
+  const uint32_t sQ = sbase;                          // tile t at sQ + t*16K
+  const uint32_t sK0 = sQ + 2 * TILE_BYTES;           // stage s: K at sK0 + s*32K, V right after K
+  const uint32_t sP = sK0 + 4 * TILE_BYTES;           // tile t at sP + t*32K
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q_tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int q0 = q_tile * BQ;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int q_base = blockIdx.x * 2 * BQ;
 
   int kv_valid = p.Tkv;
   if (p.kv_len) kv_valid = min(kv_valid, max(1, p.kv_len[b]));
-  int kv_end = kv_valid;
-  if (p.causal) kv_end = min(kv_end, q0 + BQ);
-  const int n_kv = (kv_end + BKV - 1) / BKV;
+  int n_kv[2];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int q0 = q_base + t * BQ;
+    int kv_end = kv_valid;
+    if (p.causal) kv_end = min(kv_end, q0 + BQ);
+    n_kv[t] = (q0 < p.Tq) ? (kv_end + BKV - 1) / BKV : 0;
+  }
+  const int n_max = max(n_kv[0], n_kv[1]);
 
   if (warp == 0 && lane == 0) {
     ptx::tma_prefetch_desc(&tmQ); ptx::tma_prefetch_desc(&tmK); ptx::tma_prefetch_desc(&tmV);
     ptx::mbar_init(ptx::smem_u32(&bar_q), 1);
-    ptx::mbar_init(ptx::smem_u32(&bar_s), 1);
-    ptx::mbar_init(ptx::smem_u32(&bar_p), 4);
-    ptx::mbar_init(ptx::smem_u32(&bar_pv), 1);
     for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&bar_s[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bar_p[s]), 4);
+      ptx::mbar_init(ptx::smem_u32(&bar_pv[s]), 1);
       ptx::mbar_init(ptx::smem_u32(&bar_kv_full[s]), 1);
       ptx::mbar_init(ptx::smem_u32(&bar_kv_empty[s]), 1);
     }
@@ -92,10 +105,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
   if (warp == 0) {
     if (lane == 0) {
-      const int qrow = b * p.Tq + q0;
-      ptx::mbar_arrive_expect_tx(ptx::smem_u32(&bar_q), TILE_BYTES);
-      ptx::tma_load_2d(sQ, &tmQ, ptx::smem_u32(&bar_q), h * HD, qrow);
-      for (int j = 0; j < n_kv; ++j) {
+      ptx::mbar_arrive_expect_tx(ptx::smem_u32(&bar_q), 2 * TILE_BYTES);
+      ptx::tma_load_2d(sQ, &tmQ, ptx::smem_u32(&bar_q), h * HD, b * p.Tq + q_base);  // box 64 x 256 rows
+      for (int j = 0; j < n_max; ++j) {
         const int s = j & 1;
         ptx::mbar_wait(ptx::smem_u32(&bar_kv_empty[s]), ((j >> 1) & 1) ^ 1);
         const uint32_t full = ptx::smem_u32(&bar_kv_full[s]);
@@ -106,131 +118,161 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (lane == 0 && n_max > 0) {
       constexpr uint32_t idesc_qk = ptx::umma_idesc_bf16(BQ, BKV, 0, 0);
       constexpr uint32_t idesc_pv = ptx::umma_idesc_bf16(BQ, HD, 0, 1);
-      auto issue_qk = [&](int j) {
+      auto issue_qk = [&](int t, int j) {
         const uint32_t sK = sK0 + (j & 1) * 2 * TILE_BYTES;
+        const uint32_t sQt = sQ + t * TILE_BYTES;
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
-          ptx::tc_mma_f16(tmem + S_COL, ptx::umma_smem_desc_sw128(sQ + k * 32, 16, 1024),
+          ptx::tc_mma_f16(tmem + S_COL + t * BKV, ptx::umma_smem_desc_sw128(sQt + k * 32, 16, 1024),
                           ptx::umma_smem_desc_sw128(sK + k * 32, 16, 1024), idesc_qk, k > 0);
-        ptx::tc_commit(ptx::smem_u32(&bar_s));
+        ptx::tc_commit(ptx::smem_u32(&bar_s[t]));
+      };
+      auto issue_pv = [&](int t, int j) {
+        const uint32_t sV = sK0 + (j & 1) * 2 * TILE_BYTES + TILE_BYTES;
+        const uint32_t sPt = sP + t * P_BYTES;
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k)
+          ptx::tc_mma_f16(tmem + O_COL + t * HD,
+                          ptx::umma_smem_desc_sw128(sPt + (k >> 2) * (P_BYTES / 2) + (k & 3) * 32, 16, 1024),
+                          ptx::umma_smem_desc_sw128(sV + k * 2048, BKV * 128, 1024), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+        ptx::tc_commit(ptx::smem_u32(&bar_pv[t]));
       };
       ptx::mbar_wait(ptx::smem_u32(&bar_q), 0);
       ptx::mbar_wait(ptx::smem_u32(&bar_kv_full[0]), 0);
       ptx::tc_fence_after();
-      issue_qk(0);
-      for (int j = 0; j < n_kv; ++j) {
-        const int s = j & 1;
-        ptx::mbar_wait(ptx::smem_u32(&bar_p), j & 1);   // P(j) in smem, S and PV TMEM regions free
-        ptx::tc_fence_after();
-        const uint32_t sV = sK0 + s * 2 * TILE_BYTES + TILE_BYTES;
 #pragma unroll
-        for (int k = 0; k < BKV / 16; ++k)
-          ptx::tc_mma_f16(tmem + PV_COL,
-                          ptx::umma_smem_desc_sw128(sP + (k >> 2) * (P_BYTES / 2) + (k & 3) * 32, 16, 1024),
-                          ptx::umma_smem_desc_sw128(sV + k * 2048, BKV * 128, 1024), idesc_pv, k > 0);
-        ptx::tc_commit(ptx::smem_u32(&bar_pv));
-        ptx::tc_commit(ptx::smem_u32(&bar_kv_empty[s]));
-        if (j + 1 < n_kv) {
-          ptx::mbar_wait(ptx::smem_u32(&bar_kv_full[(j + 1) & 1]), ((j + 1) >> 1) & 1);
-          ptx::tc_fence_after();
-          issue_qk(j + 1);
+      for (int t = 0; t < 2; ++t)
+        if (n_kv[t] > 0) issue_qk(t, 0);
+      for (int j = 0; j < n_max; ++j) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (j < n_kv[t]) {
+            ptx::mbar_wait(ptx::smem_u32(&bar_p[t]), j & 1);   // P_t(j) in smem, S_t read, O_t rescaled
+            ptx::tc_fence_after();
+            issue_pv(t, j);
+            if (j + 1 < n_kv[t]) {
+              ptx::mbar_wait(ptx::smem_u32(&bar_kv_full[(j + 1) & 1]), ((j + 1) >> 1) & 1);
+              ptx::tc_fence_after();
+              issue_qk(t, j + 1);
+            }
+          }
         }
+        ptx::tc_commit(ptx::smem_u32(&bar_kv_empty[j & 1]));   // K/V stage j free once both tiles' MMAs retire
       }
     }
   } else {
-    // ----------------------------- softmax / output warps -----------------------------
+    // ----------------------------- softmax / output warpgroups -----------------------------
+    const int t = (warp - 2) >> 2;                   // query tile of this warpgroup
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;               // row within the tile == TMEM lane
-    const int qi = q0 + r;                           // query index within the sequence
+    const int qi = q_base + t * BQ + r;              // query index within the sequence
     const uint32_t t_lane = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t t_s = tmem + t_lane + S_COL + t * BKV;
+    const uint32_t t_o = tmem + t_lane + O_COL + t * HD;
+    const uint32_t sPt = sP + t * P_BYTES;
     const float c = p.scale_log2;
+    const int n_t = n_kv[t];
     float m = -INFINITY, l = 0.f;
-    float o[HD];
-#pragma unroll
-    for (int i = 0; i < HD; ++i) o[i] = 0.f;
 
-    for (int j = 0; j < n_kv; ++j) {
-      ptx::mbar_wait(ptx::smem_u32(&bar_s), j & 1);
+    for (int j = 0; j < n_t; ++j) {
+      ptx::mbar_wait(ptx::smem_u32(&bar_s[t]), j & 1);
       ptx::tc_fence_after();
+      float v[BKV];
+      {
+        uint32_t (&u)[BKV] = reinterpret_cast<uint32_t (&)[BKV]>(v);
+#pragma unroll
+        for (int cc = 0; cc < BKV / 32; ++cc)
+          ptx::tc_ld_32x32b_x32(t_s + cc * 32, reinterpret_cast<uint32_t (&)[32]>(u[cc * 32]));
+        ptx::tc_wait_ld();
+      }
       const int k0 = j * BKV;
       int limit = kv_valid - k0;                     // keys [0, limit) of this tile are visible
       if (p.causal) limit = min(limit, qi - k0 + 1);
-      const bool need_mask = limit < BKV;
-      // pass 1: row maximum
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int cc = 0; cc < BKV / 32; ++cc) {
-        uint32_t v[32];
-        ptx::tc_ld_32x32b_x32(tmem + t_lane + S_COL + cc * 32, v);
-        ptx::tc_wait_ld();
+      if (limit < BKV) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = __uint_as_float(v[i]);
-          mx = fmaxf(mx, (need_mask && cc * 32 + i >= limit) ? -INFINITY : s);
+        for (int i = 0; i < BKV; ++i)
+          if (i >= limit) v[i] = -INFINITY;
+      }
+      float mx = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
+#pragma unroll
+      for (int i = 4; i < BKV; i += 2) mx = fmaxf(fmaxf(mx, v[i]), v[i + 1]);
+      const float m_new = fmaxf(m, mx);
+      const bool need = (j == 0) || ((m_new - m) * c > RESCALE_LOG2);
+      const float m_next = need ? m_new : m;
+      if (j > 0) {
+        ptx::mbar_wait(ptx::smem_u32(&bar_pv[t]), (j - 1) & 1);   // P_t*V(j-1) retired: O_t valid, sP_t reusable
+        ptx::tc_fence_after();
+        if (__any_sync(0xffffffffu, need)) {
+          const float alpha = need ? fast_exp2((m - m_next) * c) : 1.0f;
+#pragma unroll 1
+          for (int cc = 0; cc < HD / 16; ++cc) {  // 16-column chunks: the 128-register score row stays live
+            uint32_t o[16];
+            ptx::tc_ld_32x32b_x16(t_o + cc * 16, o);
+            ptx::tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            ptx::tc_st_32x32b_x16(t_o + cc * 16, o);
+          }
+          ptx::tc_wait_st();
+          l *= alpha;
         }
       }
-      const float m_new = fmaxf(m, mx);
-      const float m_off = (m_new == -INFINITY) ? 0.f : m_new * c;
-      const float alpha = (m == -INFINITY) ? 0.f : fast_exp2(m * c - m_off);
-      // pass 2: probabilities -> bf16 -> swizzled smem (A operand of P*V)
-      float rs = 0.f;
-#pragma unroll 1
-      for (int cc = 0; cc < BKV / 32; ++cc) {
-        uint32_t v[32];
-        ptx::tc_ld_32x32b_x32(tmem + t_lane + S_COL + cc * 32, v);
-        ptx::tc_wait_ld();
-        float pr[32];
+      m = m_next;
+      const float neg = (m == -INFINITY) ? 0.f : -m * c;
+      const float2 c2 = make_float2(c, c), n2 = make_float2(neg, neg);
+      float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float e = fast_exp2(__uint_as_float(v[i]) * c - m_off);
-          pr[i] = (need_mask && cc * 32 + i >= limit) ? 0.f : e;
-          rs += pr[i];
-        }
-        const uint32_t half_base = sP + (cc >> 1) * (P_BYTES / 2) + r * 128;
+      for (int cc = 0; cc < BKV / 32; ++cc) {
+        const uint32_t half_base = sPt + (cc >> 1) * (P_BYTES / 2) + r * 128;
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = cc * 32 + q4 * 8 + e * 2;
+            const float2 x = __ffma2_rn(make_float2(v[i], v[i + 1]), c2, n2);
+            const float2 pe = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+            if (e & 1) sum_b = __fadd2_rn(sum_b, pe); else sum_a = __fadd2_rn(sum_a, pe);
+            w[e] = pack_bf16x2(pe.x, pe.y);
+          }
           const int chunk = (cc & 1) * 4 + q4;       // 16-byte chunk index within the 128-byte row
           const uint32_t addr = half_base + ((chunk ^ (r & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
-                       "r"(pack_bf16x2(pr[8 * q4 + 0], pr[8 * q4 + 1])), "r"(pack_bf16x2(pr[8 * q4 + 2], pr[8 * q4 + 3])),
-                       "r"(pack_bf16x2(pr[8 * q4 + 4], pr[8 * q4 + 5])), "r"(pack_bf16x2(pr[8 * q4 + 6], pr[8 * q4 + 7]))
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
                        : "memory");
         }
       }
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_p));
-      l = l * alpha + rs;
-      m = m_new;
-      // accumulate O with this tile's P*V
-      ptx::mbar_wait(ptx::smem_u32(&bar_pv), j & 1);
-      ptx::tc_fence_after();
-#pragma unroll
-      for (int cc = 0; cc < HD / 32; ++cc) {
-        uint32_t v[32];
-        ptx::tc_ld_32x32b_x32(tmem + t_lane + PV_COL + cc * 32, v);
-        ptx::tc_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[cc * 32 + i] = o[cc * 32 + i] * alpha + __uint_as_float(v[i]);
-      }
+      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_p[t]));
+      l += (sum_a.x + sum_a.y) + (sum_b.x + sum_b.y);
     }
-    if (qi < p.Tq) {
+    if (n_t > 0) {
+      ptx::mbar_wait(ptx::smem_u32(&bar_pv[t]), (n_t - 1) & 1);
+      ptx::tc_fence_after();
       const float inv = 1.f / l;
       bf16* dst = p.o + (static_cast<int64_t>(b) * p.Tq + qi) * p.ldo + h * HD;
 #pragma unroll
-      for (int q8 = 0; q8 < HD / 8; ++q8) {
-        uint4 u;
-        u.x = pack_bf16x2(o[8 * q8 + 0] * inv, o[8 * q8 + 1] * inv);
-        u.y = pack_bf16x2(o[8 * q8 + 2] * inv, o[8 * q8 + 3] * inv);
-        u.z = pack_bf16x2(o[8 * q8 + 4] * inv, o[8 * q8 + 5] * inv);
-        u.w = pack_bf16x2(o[8 * q8 + 6] * inv, o[8 * q8 + 7] * inv);
-        reinterpret_cast<uint4*>(dst)[q8] = u;
+      for (int cc = 0; cc < HD / 32; ++cc) {
+        uint32_t o[32];
+        ptx::tc_ld_32x32b_x32(t_o + cc * 32, o);
+        ptx::tc_wait_ld();
+        if (qi < p.Tq) {
+#pragma unroll
+          for (int q8 = 0; q8 < 4; ++q8) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(o[8 * q8 + 0]) * inv, __uint_as_float(o[8 * q8 + 1]) * inv);
+            u.y = pack_bf16x2(__uint_as_float(o[8 * q8 + 2]) * inv, __uint_as_float(o[8 * q8 + 3]) * inv);
+            u.z = pack_bf16x2(__uint_as_float(o[8 * q8 + 4]) * inv, __uint_as_float(o[8 * q8 + 5]) * inv);
+            u.w = pack_bf16x2(__uint_as_float(o[8 * q8 + 6]) * inv, __uint_as_float(o[8 * q8 + 7]) * inv);
+            reinterpret_cast<uint4*>(dst + cc * 32)[q8] = u;
+          }
+        }
       }
-      if (p.lse) p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Tq + qi] = m * c + log2f(l);
+      if (qi < p.Tq && p.lse) p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Tq + qi] = m * c + log2f(l);
     }
   }
 
@@ -256,7 +298,7 @@ extern "C" int oasr_attention_fwd(const void* q, int64_t ldq, const void* k, int
   OASR_REQUIRE(!causal || Tq == Tkv, "attention: causal needs Tq == Tkv");
   CUtensorMap tmQ, tmK, tmV;
   int rc;
-  if ((rc = make_tmap_2d(&tmQ, q, 2, (uint64_t)(H * HD), (uint64_t)(B * Tq), (uint64_t)ldq * 2, HD, BQ, true))) return rc;
+  if ((rc = make_tmap_2d(&tmQ, q, 2, (uint64_t)(H * HD), (uint64_t)(B * Tq), (uint64_t)ldq * 2, HD, 2 * BQ, true))) return rc;
   if ((rc = make_tmap_2d(&tmK, k, 2, (uint64_t)(H * HD), (uint64_t)(B * Tkv), (uint64_t)ldk * 2, HD, BKV, true))) return rc;
   if ((rc = make_tmap_2d(&tmV, v, 2, (uint64_t)(H * HD), (uint64_t)(B * Tkv), (uint64_t)ldv * 2, HD, BKV, true))) return rc;
   AttnParams p;
@@ -268,8 +310,8 @@ extern "C" int oasr_attention_fwd(const void* q, int64_t ldq, const void* k, int
     OASR_CUDA_OK(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     attr_set = true;
   }
-  dim3 grid((unsigned)ceil_div(Tq, BQ), (unsigned)H, (unsigned)B);
-  attention_fwd_kernel<<<grid, 192, ATT_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+  dim3 grid((unsigned)ceil_div(Tq, 2 * BQ), (unsigned)H, (unsigned)B);
+  attention_fwd_kernel<<<grid, 320, ATT_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
   OASR_LAUNCH_CHECK();
   return OASR_OK;
 }
