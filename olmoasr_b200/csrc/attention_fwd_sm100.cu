@@ -15,7 +15,7 @@
 // TMEM (512 cols): S0 0..127 | S1 128..255 | O0 256..319 | O1 320..383.  O is accumulated by the P*V MMAs
 // directly in TMEM; it is rescaled (tcgen05.ld -> scale -> tcgen05.st) only when a row maximum grows by more
 // than 2^8 -- otherwise the stale maximum is kept (probabilities stay <= 256, exact in bf16/fp32 terms).
-// The score row is read from TMEM once and kept in registers; scale/subtract and the row sum use packed
+// Half of the score row stays in registers between the max and exp passes; scale/subtract and the row sum use packed
 // FFMA2 / FADD2, the maximum FMNMX3.  P goes to smem as bf16 in the 128B-swizzled K-major layout and is the
 // A operand of the P*V MMA; V is consumed MN-major straight from its TMA tile.
 #include "common.cuh"
@@ -45,7 +45,7 @@ struct AttnParams {
   float scale_log2;  // scale * log2(e)
 };
 
-__global__ void __maxnreg__(200)
+__global__ void __launch_bounds__(320, 1)  // 10 warps are allocated as 12: <= 168 registers per thread
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -180,25 +180,41 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     for (int j = 0; j < n_t; ++j) {
       ptx::mbar_wait(ptx::smem_u32(&bar_s[t]), j & 1);
       ptx::tc_fence_after();
-      float v[BKV];
-      {
-        uint32_t (&u)[BKV] = reinterpret_cast<uint32_t (&)[BKV]>(v);
-#pragma unroll
-        for (int cc = 0; cc < BKV / 32; ++cc)
-          ptx::tc_ld_32x32b_x32(t_s + cc * 32, reinterpret_cast<uint32_t (&)[32]>(u[cc * 32]));
-        ptx::tc_wait_ld();
-      }
+      // Pass 1: row maximum.  Columns 0..63 stay in registers; 64..127 are re-read from TMEM in pass 2 (holding all
+      // 128 would need ~190 registers, and a 10-warp CTA is limited to 168).
       const int k0 = j * BKV;
       int limit = kv_valid - k0;                     // keys [0, limit) of this tile are visible
       if (p.causal) limit = min(limit, qi - k0 + 1);
-      if (limit < BKV) {
+      const bool masked = limit < BKV;
+      float v[64];
+      float mx;
+      {
+        uint32_t (&u)[64] = reinterpret_cast<uint32_t (&)[64]>(v);
+        ptx::tc_ld_32x32b_x32(t_s, reinterpret_cast<uint32_t (&)[32]>(u[0]));
+        ptx::tc_ld_32x32b_x32(t_s + 32, reinterpret_cast<uint32_t (&)[32]>(u[32]));
+        ptx::tc_wait_ld();
+        if (masked) {
 #pragma unroll
-        for (int i = 0; i < BKV; ++i)
-          if (i >= limit) v[i] = -INFINITY;
+          for (int i = 0; i < 64; ++i)
+            if (i >= limit) v[i] = -INFINITY;
+        }
+        mx = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
+#pragma unroll
+        for (int i = 4; i < 64; i += 2) mx = fmaxf(fmaxf(mx, v[i]), v[i + 1]);
+#pragma unroll 1
+        for (int cc = 2; cc < 4; ++cc) {
+          uint32_t w[32];
+          ptx::tc_ld_32x32b_x32(t_s + cc * 32, w);
+          ptx::tc_wait_ld();
+          if (masked) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (cc * 32 + i >= limit) w[i] = 0xff800000u;  // -inf
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) mx = fmaxf(fmaxf(mx, __uint_as_float(w[i])), __uint_as_float(w[i + 1]));
+        }
       }
-      float mx = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
-#pragma unroll
-      for (int i = 4; i < BKV; i += 2) mx = fmaxf(fmaxf(mx, v[i]), v[i + 1]);
       const float m_new = fmaxf(m, mx);
       const bool need = (j == 0) || ((m_new - m) * c > RESCALE_LOG2);
       const float m_next = need ? m_new : m;
@@ -208,7 +224,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         if (__any_sync(0xffffffffu, need)) {
           const float alpha = need ? fast_exp2((m - m_next) * c) : 1.0f;
 #pragma unroll 1
-          for (int cc = 0; cc < HD / 16; ++cc) {  // 16-column chunks: the 128-register score row stays live
+          for (int cc = 0; cc < HD / 16; ++cc) {  // 16-column chunks keep the register peak low
             uint32_t o[16];
             ptx::tc_ld_32x32b_x16(t_o + cc * 16, o);
             ptx::tc_wait_ld();
@@ -221,19 +237,19 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
       }
       m = m_next;
+      // Pass 2: p = 2^(s*c - m*c) (packed FFMA2), row sum (FADD2), bf16 -> swizzled smem (A operand of P*V)
       const float neg = (m == -INFINITY) ? 0.f : -m * c;
       const float2 c2 = make_float2(c, c), n2 = make_float2(neg, neg);
       float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int cc = 0; cc < BKV / 32; ++cc) {
+      auto emit32 = [&](const float* x32, int cc) {
         const uint32_t half_base = sPt + (cc >> 1) * (P_BYTES / 2) + r * 128;
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
           uint32_t w[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int i = cc * 32 + q4 * 8 + e * 2;
-            const float2 x = __ffma2_rn(make_float2(v[i], v[i + 1]), c2, n2);
+            const int i = q4 * 8 + e * 2;
+            const float2 x = __ffma2_rn(make_float2(x32[i], x32[i + 1]), c2, n2);
             const float2 pe = make_float2(fast_exp2(x.x), fast_exp2(x.y));
             if (e & 1) sum_b = __fadd2_rn(sum_b, pe); else sum_a = __fadd2_rn(sum_a, pe);
             w[e] = pack_bf16x2(pe.x, pe.y);
@@ -243,6 +259,20 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
                        : "memory");
         }
+      };
+      emit32(&v[0], 0);
+      emit32(&v[32], 1);
+#pragma unroll 1
+      for (int cc = 2; cc < 4; ++cc) {
+        float x32[32];
+        ptx::tc_ld_32x32b_x32(t_s + cc * 32, reinterpret_cast<uint32_t (&)[32]>(x32));
+        ptx::tc_wait_ld();
+        if (masked) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (cc * 32 + i >= limit) x32[i] = -INFINITY;
+        }
+        emit32(x32, cc);
       }
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
