@@ -11,8 +11,8 @@
 //                                                             the "transposes" are MN-major descriptors)
 // dV and dK stay resident in TMEM for the whole loop; dQ_i is drained per query tile and reduced across
 // key tiles with vectorised fp32 red.global.add into a scratch buffer (converted to bf16 afterwards).
-// 320 threads: TMA warp, MMA warp, 8 compute warps (two per TMEM lane quarter, each taking half of the 128 key
-// columns; packed FFMA2 / FADD2 / FMUL2 math).
+// 8 compute warps (two per TMEM lane quarter, each taking half of the 128 key columns; packed FFMA2 / FADD2 /
+// FMUL2 math) + TMA warp + MMA warp; S / dP are released to the MMA warp as soon as they sit in registers.
 // TMEM map (512 cols): S 0..127 | dP 128..255 | dV 256..319 | dK 320..383 | dQ 384..447.
 #include "common.cuh"
 #include "ptx_sm100.cuh"
@@ -23,13 +23,15 @@ namespace {
 constexpr int HD = 64;
 constexpr int BQ = 128;
 constexpr int BKV = 128;
+constexpr int Q_STAGES = 3;
 constexpr int TILE_BYTES = 128 * HD * 2;  // 16 KB
 constexpr int P_BYTES = BQ * BKV * 2;     // 32 KB
-// K, V, Q[2], dO[2], P, dS
-constexpr int BWD_TILES = 2 * TILE_BYTES + 4 * TILE_BYTES + 2 * P_BYTES;  // 160 KB
-constexpr int BWD_SMEM = BWD_TILES + 128;
+// K, V, (Q, dO) x Q_STAGES, P, dS
+constexpr int BWD_TILES = 2 * TILE_BYTES + Q_STAGES * 2 * TILE_BYTES + 2 * P_BYTES;  // 192 KB
+constexpr int BWD_SMEM = BWD_TILES + 256;
 constexpr int TMEM_COLS = 512;
 constexpr int S_COL = 0, DP_COL = 128, DV_COL = 256, DK_COL = 320, DQ_COL = 384;
+constexpr int COMPUTE_REGS = 192, CONTROL_REGS = 120;   // 8 * 192 + 4 * 120 == 12 * 168 (no spills in either role)
 
 struct BwdParams {
   const float* lse;   // (B,H,Tq) log2 domain
@@ -58,20 +60,25 @@ __device__ __forceinline__ void store_swizzled_row32(uint32_t tile_base, int r, 
   }
 }
 
-__global__ void __launch_bounds__(320, 1)
+// 384 threads: warps 0..7 compute (warp w: TMEM lane quarter w%4, key-column half w/4), warp 8 TMA producer,
+// warp 9 MMA issuer + TMEM owner, warps 10-11 idle.  setmaxnreg gives the compute warps 224 registers so that a
+// thread holds its 64 S and 64 dP values at once: both TMEM buffers are released right after the load (bar_free) and
+// the MMA warp issues S / dP of the NEXT query tile underneath this tile's exp / dS math.
+__global__ void __launch_bounds__(384, 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                      const BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + BWD_TILES);
   uint64_t& bar_kv = bars[0];
-  uint64_t& bar_sdp = bars[1];
-  uint64_t& bar_pds = bars[2];
-  uint64_t& bar_dq = bars[3];
-  uint64_t& bar_done = bars[4];
-  uint64_t* bar_q_full = bars + 5;
-  uint64_t* bar_q_empty = bars + 7;
-  uint32_t& tmem_slot = *reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t& bar_sdp = bars[1];    // S, dP ready (MMA commit)
+  uint64_t& bar_free = bars[2];   // S, dP read into registers (8 warp arrivals)
+  uint64_t& bar_pds = bars[3];    // P, dS in smem (8 warp arrivals)
+  uint64_t& bar_dq = bars[4];     // dV / dK / dQ MMAs of this tile retired (MMA commit)
+  uint64_t& bar_done = bars[5];
+  uint64_t* bar_q_full = bars + 6;
+  uint64_t* bar_q_empty = bars + 6 + Q_STAGES;
+  uint32_t& tmem_slot = *reinterpret_cast<uint32_t*>(bars + 6 + 2 * Q_STAGES);
 
   const uint32_t sbase = ptx::smem_u32(smem_raw);
   if ((sbase & 1023u) != 0) {
@@ -80,7 +87,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
   const uint32_t sK = sbase, sV = sK + TILE_BYTES;
   const uint32_t sQ0 = sV + TILE_BYTES;            // stage s: Q at sQ0 + s*32K, dO right after
-  const uint32_t sP = sQ0 + 4 * TILE_BYTES, sdS = sP + P_BYTES;
+  const uint32_t sP = sQ0 + Q_STAGES * 2 * TILE_BYTES, sdS = sP + P_BYTES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kv_tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int kv0 = kv_tile * BKV;
@@ -92,20 +99,21 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const int i_end = (kv0 < kv_valid) ? n_q_tiles : i_begin;  // fully masked key tile: no work, zero grads
   const int n_iter = i_end - i_begin;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     ptx::tma_prefetch_desc(&tmQ); ptx::tma_prefetch_desc(&tmK); ptx::tma_prefetch_desc(&tmV); ptx::tma_prefetch_desc(&tmdO);
     ptx::mbar_init(ptx::smem_u32(&bar_kv), 1);
     ptx::mbar_init(ptx::smem_u32(&bar_sdp), 1);
+    ptx::mbar_init(ptx::smem_u32(&bar_free), 8);
     ptx::mbar_init(ptx::smem_u32(&bar_pds), 8);
     ptx::mbar_init(ptx::smem_u32(&bar_dq), 1);
     ptx::mbar_init(ptx::smem_u32(&bar_done), 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < Q_STAGES; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bar_q_full[s]), 1);
       ptx::mbar_init(ptx::smem_u32(&bar_q_empty[s]), 1);
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == 9) {
     ptx::tmem_alloc<TMEM_COLS>(ptx::smem_u32(&tmem_slot));
     ptx::tmem_relinquish();
   }
@@ -114,28 +122,31 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   ptx::tc_fence_after();
   const uint32_t tmem = tmem_slot;
 
-  if (warp == 0) {
-    if (lane == 0 && n_iter > 0) {
+  if (warp >= 8) {
+    ptx::setmaxnreg_dec<CONTROL_REGS>();
+    if (warp == 8 && lane == 0 && n_iter > 0) {
+      // ------------------------------ TMA producer ------------------------------
       ptx::mbar_arrive_expect_tx(ptx::smem_u32(&bar_kv), 2 * TILE_BYTES);
       ptx::tma_load_2d(sK, &tmK, ptx::smem_u32(&bar_kv), h * HD, b * p.Tkv + kv0);
       ptx::tma_load_2d(sV, &tmV, ptx::smem_u32(&bar_kv), h * HD, b * p.Tkv + kv0);
+      int s = 0;
+      uint32_t ph = 0;
       for (int it = 0; it < n_iter; ++it) {
-        const int s = it & 1;
-        ptx::mbar_wait(ptx::smem_u32(&bar_q_empty[s]), ((it >> 1) & 1) ^ 1);
+        ptx::mbar_wait(ptx::smem_u32(&bar_q_empty[s]), ph ^ 1);
         const uint32_t full = ptx::smem_u32(&bar_q_full[s]);
         ptx::mbar_arrive_expect_tx(full, 2 * TILE_BYTES);
         const int qrow = b * p.Tq + (i_begin + it) * BQ;
         ptx::tma_load_2d(sQ0 + s * 2 * TILE_BYTES, &tmQ, full, h * HD, qrow);
         ptx::tma_load_2d(sQ0 + s * 2 * TILE_BYTES + TILE_BYTES, &tmdO, full, h * HD, qrow);
+        if (++s == Q_STAGES) { s = 0; ph ^= 1; }
       }
-    }
-  } else if (warp == 1) {
-    if (lane == 0 && n_iter > 0) {
+    } else if (warp == 9 && lane == 0 && n_iter > 0) {
+      // ------------------------------ MMA issuer ------------------------------
       constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, 128, 0, 0);    // S, dP
       constexpr uint32_t idesc_kv = ptx::umma_idesc_bf16(128, 64, 1, 1);    // dV, dK
       constexpr uint32_t idesc_dq = ptx::umma_idesc_bf16(128, 64, 0, 1);    // dQ
-      auto issue_s_dp = [&](int it) {
-        const uint32_t sQ = sQ0 + (it & 1) * 2 * TILE_BYTES, sdO = sQ + TILE_BYTES;
+      auto issue_s_dp = [&](int stage) {
+        const uint32_t sQ = sQ0 + stage * 2 * TILE_BYTES, sdO = sQ + TILE_BYTES;
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
           ptx::tc_mma_f16(tmem + S_COL, ptx::umma_smem_desc_sw128(sQ + k * 32, 16, 1024),
@@ -150,10 +161,20 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       ptx::mbar_wait(ptx::smem_u32(&bar_q_full[0]), 0);
       ptx::tc_fence_after();
       issue_s_dp(0);
+      int st = 0;
+      uint32_t st_ph = 0;
       for (int it = 0; it < n_iter; ++it) {
-        const int s = it & 1;
-        const uint32_t sQ = sQ0 + s * 2 * TILE_BYTES, sdO = sQ + TILE_BYTES;
-        ptx::mbar_wait(ptx::smem_u32(&bar_pds), it & 1);  // P, dS in smem; S/dP/dQ TMEM regions drained
+        int st_n = st + 1;
+        uint32_t ph_n = st_ph;
+        if (st_n == Q_STAGES) { st_n = 0; ph_n ^= 1; }
+        if (it + 1 < n_iter) {   // next tile's S / dP as soon as this tile's have been read into registers
+          ptx::mbar_wait(ptx::smem_u32(&bar_q_full[st_n]), ph_n);
+          ptx::mbar_wait(ptx::smem_u32(&bar_free), it & 1);
+          ptx::tc_fence_after();
+          issue_s_dp(st_n);
+        }
+        const uint32_t sQ = sQ0 + st * 2 * TILE_BYTES, sdO = sQ + TILE_BYTES;
+        ptx::mbar_wait(ptx::smem_u32(&bar_pds), it & 1);  // P, dS in smem; dQ TMEM drained
         ptx::tc_fence_after();
 #pragma unroll
         for (int k = 0; k < BQ / 16; ++k) {  // reduction over the 128 query rows, 16 at a time
@@ -170,23 +191,40 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                           ptx::umma_smem_desc_sw128(sdS + (k >> 2) * (P_BYTES / 2) + (k & 3) * 32, 16, 1024),
                           ptx::umma_smem_desc_sw128(sK + k * 2048, BKV * 128, 1024), idesc_dq, k > 0);
         ptx::tc_commit(ptx::smem_u32(&bar_dq));
-        ptx::tc_commit(ptx::smem_u32(&bar_q_empty[s]));
-        if (it + 1 < n_iter) {
-          ptx::mbar_wait(ptx::smem_u32(&bar_q_full[(it + 1) & 1]), ((it + 1) >> 1) & 1);
-          ptx::tc_fence_after();
-          issue_s_dp(it + 1);
-        }
+        ptx::tc_commit(ptx::smem_u32(&bar_q_empty[st]));
+        st = st_n; st_ph = ph_n;
       }
       ptx::tc_commit(ptx::smem_u32(&bar_done));
     }
   } else {
     // ----------------------------- compute warps -----------------------------
-    // 8 warps: warp w owns TMEM lanes 32*(w%4).. (query row r = key row r for dK/dV) and the column half (w-2)/4
+    ptx::setmaxnreg_inc<COMPUTE_REGS>();
     const int quarter = warp & 3;
-    const int chalf = (warp - 2) >> 2;
+    const int chalf = warp >> 2;
     const int r = quarter * 32 + lane;
     const uint32_t t_lane = static_cast<uint32_t>(quarter * 32) << 16;
     const float c = p.scale_log2;
+
+    auto drain_dq = [&](int it) {   // dQ of query tile `it`: this warp's 32 of the 64 columns, fp32 red.add
+      const int qi = (i_begin + it) * BQ + r;
+      ptx::mbar_wait(ptx::smem_u32(&bar_dq), it & 1);
+      ptx::tc_fence_after();
+      uint32_t v[32];
+      ptx::tc_ld_32x32b_x32(tmem + t_lane + DQ_COL + chalf * 32, v);
+      ptx::tc_wait_ld();
+      if (qi < p.Tq) {
+        float* dq_row = p.dq_accum + (static_cast<int64_t>(b) * p.Tq + qi) * (p.H * HD) + h * HD + chalf * 32;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                       ::"l"(dq_row + 4 * j), "f"(__uint_as_float(v[4 * j]) * p.scale),
+                         "f"(__uint_as_float(v[4 * j + 1]) * p.scale), "f"(__uint_as_float(v[4 * j + 2]) * p.scale),
+                         "f"(__uint_as_float(v[4 * j + 3]) * p.scale)
+                       : "memory");
+      }
+      ptx::tc_fence_before();
+    };
+
     for (int it = 0; it < n_iter; ++it) {
       const int q0 = (i_begin + it) * BQ;
       const int qi = q0 + r;
@@ -199,24 +237,32 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       if (!q_ok) limit = 0;
       ptx::mbar_wait(ptx::smem_u32(&bar_sdp), it & 1);
       ptx::tc_fence_after();
+      uint32_t sv[64], dv[64];
+      ptx::tc_ld_32x32b_x32(tmem + t_lane + S_COL + chalf * 64, reinterpret_cast<uint32_t (&)[32]>(sv[0]));
+      ptx::tc_ld_32x32b_x32(tmem + t_lane + S_COL + chalf * 64 + 32, reinterpret_cast<uint32_t (&)[32]>(sv[32]));
+      ptx::tc_ld_32x32b_x32(tmem + t_lane + DP_COL + chalf * 64, reinterpret_cast<uint32_t (&)[32]>(dv[0]));
+      ptx::tc_ld_32x32b_x32(tmem + t_lane + DP_COL + chalf * 64 + 32, reinterpret_cast<uint32_t (&)[32]>(dv[32]));
+      ptx::tc_wait_ld();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_free));   // S / dP TMEM may be overwritten
+      if (it > 0) drain_dq(it - 1);   // also: dV/dK/dQ MMAs of the previous tile retired => sP / sdS reusable
+
       const float2 c2 = make_float2(c, c), nl2 = make_float2(-lse, -lse), nd2 = make_float2(-dlt, -dlt);
-#pragma unroll 1
-      for (int cc = chalf * 2; cc < chalf * 2 + 2; ++cc) {
-        uint32_t sv[32], dv[32];
-        ptx::tc_ld_32x32b_x32(tmem + t_lane + S_COL + cc * 32, sv);
-        ptx::tc_ld_32x32b_x32(tmem + t_lane + DP_COL + cc * 32, dv);
-        ptx::tc_wait_ld();
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int cc = chalf * 2 + hh;
         float pr[32], ds[32];
         const bool full = (cc + 1) * 32 <= limit;
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), c2, nl2);
+          const float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[hh * 32 + i]), __uint_as_float(sv[hh * 32 + i + 1])), c2, nl2);
           float2 pe = make_float2(fast_exp2(x.x), fast_exp2(x.y));
           if (!full) {
             if (cc * 32 + i >= limit) pe.x = 0.f;
             if (cc * 32 + i + 1 >= limit) pe.y = 0.f;
           }
-          const float2 dd = __fadd2_rn(make_float2(__uint_as_float(dv[i]), __uint_as_float(dv[i + 1])), nd2);
+          const float2 dd = __fadd2_rn(make_float2(__uint_as_float(dv[hh * 32 + i]), __uint_as_float(dv[hh * 32 + i + 1])), nd2);
           const float2 dsv = __fmul2_rn(pe, dd);
           pr[i] = pe.x; pr[i + 1] = pe.y;
           ds[i] = dsv.x; ds[i + 1] = dsv.y;
@@ -228,28 +274,10 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_pds));
-      // drain dQ_i
-      ptx::mbar_wait(ptx::smem_u32(&bar_dq), it & 1);
-      ptx::tc_fence_after();
-      float* dq_row = p.dq_accum + (static_cast<int64_t>(b) * p.Tq + qi) * (p.H * HD) + h * HD;
-      {
-        const int cc = chalf;
-        uint32_t v[32];
-        ptx::tc_ld_32x32b_x32(tmem + t_lane + DQ_COL + cc * 32, v);
-        ptx::tc_wait_ld();
-        if (q_ok) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
-                         ::"l"(dq_row + cc * 32 + 4 * j), "f"(__uint_as_float(v[4 * j]) * p.scale),
-                           "f"(__uint_as_float(v[4 * j + 1]) * p.scale), "f"(__uint_as_float(v[4 * j + 2]) * p.scale),
-                           "f"(__uint_as_float(v[4 * j + 3]) * p.scale)
-                         : "memory");
-        }
-      }
-      ptx::tc_fence_before();
     }
-    // ---- dK / dV for key row r of this tile
+    if (n_iter > 0) drain_dq(n_iter - 1);
+
+    // ---- dK / dV for key row r of this tile (this warp's 32 of the 64 columns)
     const int ki = kv0 + r;
     if (n_iter > 0) {
       ptx::mbar_wait(ptx::smem_u32(&bar_done), 0);
@@ -289,7 +317,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 9) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<TMEM_COLS>(tmem);
   }
@@ -379,7 +407,7 @@ extern "C" int oasr_attention_bwd(const void* q, int64_t ldq, const void* k, int
     attr_set = true;
   }
   dim3 grid((unsigned)ceil_div(Tkv, BKV), (unsigned)H, (unsigned)B);
-  attention_bwd_kernel<<<grid, 320, BWD_SMEM, st>>>(tmQ, tmK, tmV, tmdO, p);
+  attention_bwd_kernel<<<grid, 384, BWD_SMEM, st>>>(tmQ, tmK, tmV, tmdO, p);
   OASR_LAUNCH_CHECK();
   const int64_t rows = B * Tq;
   int64_t blocks = ceil_div(rows * (H * HD / 8), 256);

@@ -41,6 +41,7 @@ struct GemmParams {
   int tiles_m, tiles_n, splits;
   int kblocks_total, kblocks_per_split;
   int epi;
+  int raster_m;  // 1: consecutive tiles walk M first (B tile stays hot in L2) -- used when B is the larger operand
 };
 
 template <int BN>
@@ -85,6 +86,22 @@ __device__ __forceinline__ void load_bf16x32(const bf16* src, float (&x)[32], in
 #pragma unroll
     for (int j = 0; j < 32; ++j) x[j] = (j < nvalid) ? __bfloat162float(src[j]) : 0.f;
   }
+}
+
+// tile index -> (m block of this CTA, n block, k split).  Default order walks N fastest: the CTAs running together share
+// A row panels and keep the (small) weight matrix in L2; raster_m walks M fastest for wide outputs (tied logits).
+__device__ __forceinline__ void decode_tile(int tile, const GemmParams& p, int tiles_mc, int cluster, int cta_rank,
+                                            int& m_blk, int& n_blk, int& split) {
+  int mc;
+  if (p.raster_m) {
+    mc = tile % tiles_mc;
+    n_blk = (tile / tiles_mc) % p.tiles_n;
+  } else {
+    n_blk = tile % p.tiles_n;
+    mc = (tile / p.tiles_n) % tiles_mc;
+  }
+  split = tile / (p.tiles_n * tiles_mc);
+  m_blk = mc * cluster + cta_rank;
 }
 
 template <int BN, int A_MN, int B_MN, int CLUSTER>
@@ -145,9 +162,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        const int n_blk = tile % p.tiles_n;
-        const int m_blk = ((tile / p.tiles_n) % tiles_mc) * CLUSTER + cta_rank;
-        const int split = tile / (p.tiles_n * tiles_mc);
+        int n_blk, m_blk, split;
+        decode_tile(tile, p, tiles_mc, CLUSTER, cta_rank, m_blk, n_blk, split);
         const int kb0 = split * p.kblocks_per_split;
         const int kb1 = min(kb0 + p.kblocks_per_split, p.kblocks_total);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -241,8 +257,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const bool vec_c = c_is_f32 ? ((p.ldc & 3) == 0) : ((p.ldc & 7) == 0);
     const bool vec_aux = (p.ldaux & 7) == 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-      const int n_blk = tile % p.tiles_n;
-      const int m_blk = ((tile / p.tiles_n) % tiles_mc) * CLUSTER + cta_rank;
+      int n_blk, m_blk, split_unused;
+      decode_tile(tile, p, tiles_mc, CLUSTER, cta_rank, m_blk, n_blk, split_unused);
       const int row = m_blk * BM + row_in_tile;
       const bool row_ok = row < p.M;
       if (p.bias != nullptr) {  // stage this tile's bias once (rounded to bf16 like bias.to(x.dtype) unless fp32 output)
@@ -428,6 +444,7 @@ extern "C" int oasr_gemm_bf16(const void* A, int64_t lda, int a_layout, const vo
   p.kblocks_per_split = (int)ceil_div(p.kblocks_total, split_k);
   p.splits = (int)ceil_div(p.kblocks_total, p.kblocks_per_split);
   p.epi = epilogue;
+  p.raster_m = (N > M) ? 1 : 0;
 
   CUtensorMap tmA, tmB;
   int rc;
