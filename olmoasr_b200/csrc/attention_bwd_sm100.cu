@@ -9,8 +9,10 @@
 //     P  = exp2(S c - LSE)  dS = P o (dP - D)                (thread r owns query row r: no reductions)
 //     dV += P^T dO          dK += dS^T Q        dQ_i = dS K  (P / dS go through swizzled smem as bf16;
 //                                                             the "transposes" are MN-major descriptors)
-// dV and dK stay resident in TMEM for the whole loop; dQ_i is drained per query tile and reduced across
-// key tiles with vectorised fp32 red.global.add into a scratch buffer (converted to bf16 afterwards).
+// dV and dK stay resident in TMEM for the whole loop; dQ_i is drained per query tile into a swizzled fp32 smem tile
+// and reduced across key tiles with ONE bulk TMA reduce-add per 32-column half (cp.reduce.async.bulk.tensor .add)
+// into an fp32 scratch buffer (converted to bf16 afterwards).  (Per-thread red.global.add.v4 made the whole kernel
+// atomics-bound: ~6500 cycles per tile pair against ~1300 of tensor work.)
 // 8 compute warps (two per TMEM lane quarter, each taking half of the 128 key columns; packed FFMA2 / FADD2 /
 // FMUL2 math) + TMA warp + MMA warp; S / dP are released to the MMA warp as soon as they sit in registers.
 // TMEM map (512 cols): S 0..127 | dP 128..255 | dV 256..319 | dK 320..383 | dQ 384..447.
@@ -27,7 +29,8 @@ constexpr int Q_STAGES = 3;
 constexpr int TILE_BYTES = 128 * HD * 2;  // 16 KB
 constexpr int P_BYTES = BQ * BKV * 2;     // 32 KB
 // K, V, (Q, dO) x Q_STAGES, P, dS
-constexpr int BWD_TILES = 2 * TILE_BYTES + Q_STAGES * 2 * TILE_BYTES + 2 * P_BYTES;  // 192 KB
+constexpr int DQ_BYTES = BQ * HD * 4;      // 32 KB fp32 staging of dQ_i: two 32-column halves of [128][128B], swizzled
+constexpr int BWD_TILES = 2 * TILE_BYTES + Q_STAGES * 2 * TILE_BYTES + 2 * P_BYTES + DQ_BYTES;  // 224 KB
 constexpr int BWD_SMEM = BWD_TILES + 256;
 constexpr int TMEM_COLS = 512;
 constexpr int S_COL = 0, DP_COL = 128, DV_COL = 256, DK_COL = 320, DQ_COL = 384;
@@ -67,7 +70,7 @@ __device__ __forceinline__ void store_swizzled_row32(uint32_t tile_base, int r, 
 __global__ void __launch_bounds__(384, 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
-                     const BwdParams p) {
+                     const __grid_constant__ CUtensorMap tmDQ, const BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + BWD_TILES);
   uint64_t& bar_kv = bars[0];
@@ -87,7 +90,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
   const uint32_t sK = sbase, sV = sK + TILE_BYTES;
   const uint32_t sQ0 = sV + TILE_BYTES;            // stage s: Q at sQ0 + s*32K, dO right after
-  const uint32_t sP = sQ0 + Q_STAGES * 2 * TILE_BYTES, sdS = sP + P_BYTES;
+  const uint32_t sP = sQ0 + Q_STAGES * 2 * TILE_BYTES, sdS = sP + P_BYTES, sDQ = sdS + P_BYTES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kv_tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int kv0 = kv_tile * BKV;
@@ -101,6 +104,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
   if (warp == 8 && lane == 0) {
     ptx::tma_prefetch_desc(&tmQ); ptx::tma_prefetch_desc(&tmK); ptx::tma_prefetch_desc(&tmV); ptx::tma_prefetch_desc(&tmdO);
+    ptx::tma_prefetch_desc(&tmDQ);
     ptx::mbar_init(ptx::smem_u32(&bar_kv), 1);
     ptx::mbar_init(ptx::smem_u32(&bar_sdp), 1);
     ptx::mbar_init(ptx::smem_u32(&bar_free), 8);
@@ -205,24 +209,34 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const uint32_t t_lane = static_cast<uint32_t>(quarter * 32) << 16;
     const float c = p.scale_log2;
 
-    auto drain_dq = [&](int it) {   // dQ of query tile `it`: this warp's 32 of the 64 columns, fp32 red.add
-      const int qi = (i_begin + it) * BQ + r;
+    // dQ of query tile `it`: this warp's 32 of the 64 columns -> swizzled fp32 smem rows -> one TMA reduce-add per
+    // column half (128 threads = the 4 warps sharing `chalf` cooperate through named barrier 1 + chalf)
+    const uint32_t sDQh = sDQ + chalf * (DQ_BYTES / 2);
+    const bool issuer = (quarter == 0 && lane == 0);
+    auto drain_dq = [&](int it) {
       ptx::mbar_wait(ptx::smem_u32(&bar_dq), it & 1);
       ptx::tc_fence_after();
       uint32_t v[32];
       ptx::tc_ld_32x32b_x32(tmem + t_lane + DQ_COL + chalf * 32, v);
       ptx::tc_wait_ld();
-      if (qi < p.Tq) {
-        float* dq_row = p.dq_accum + (static_cast<int64_t>(b) * p.Tq + qi) * (p.H * HD) + h * HD + chalf * 32;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
-                       ::"l"(dq_row + 4 * j), "f"(__uint_as_float(v[4 * j]) * p.scale),
-                         "f"(__uint_as_float(v[4 * j + 1]) * p.scale), "f"(__uint_as_float(v[4 * j + 2]) * p.scale),
-                         "f"(__uint_as_float(v[4 * j + 3]) * p.scale)
-                       : "memory");
-      }
       ptx::tc_fence_before();
+      if (issuer) ptx::tma_store_wait_read<0>();               // previous reduce has finished reading the staging tile
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + chalf) : "memory");
+#pragma unroll
+      for (int q4 = 0; q4 < 8; ++q4) {
+        const uint32_t addr = sDQh + r * 128 + ((q4 ^ (r & 7)) << 4);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(__uint_as_float(v[4 * q4]) * p.scale),
+                     "f"(__uint_as_float(v[4 * q4 + 1]) * p.scale), "f"(__uint_as_float(v[4 * q4 + 2]) * p.scale),
+                     "f"(__uint_as_float(v[4 * q4 + 3]) * p.scale)
+                     : "memory");
+      }
+      ptx::fence_proxy_async_smem();
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + chalf) : "memory");
+      if (issuer) {
+        // rows past Tq carry exact zeros (their P and dS rows are zero), rows past the tensor are clipped by TMA
+        ptx::tma_reduce_add_2d(&tmDQ, sDQh, h * HD + chalf * 32, b * p.Tq + (i_begin + it) * BQ);
+        ptx::tma_store_commit();
+      }
     };
 
     for (int it = 0; it < n_iter; ++it) {
@@ -275,7 +289,10 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_pds));
     }
-    if (n_iter > 0) drain_dq(n_iter - 1);
+    if (n_iter > 0) {
+      drain_dq(n_iter - 1);
+      if (issuer) ptx::tma_store_wait_read<0>();
+    }
 
     // ---- dK / dV for key row r of this tile (this warp's 32 of the 64 columns)
     const int ki = kv0 + r;
@@ -384,12 +401,13 @@ extern "C" int oasr_attention_bwd(const void* q, int64_t ldq, const void* k, int
   OASR_REQUIRE(((ldq | ldk | ldv | ldo | lddo | lddq | lddk | lddv) & 7) == 0, "attention_bwd: strides must be multiples of 8");
   OASR_REQUIRE(!causal || Tq == Tkv, "attention_bwd: causal needs Tq == Tkv");
   cudaStream_t st = (cudaStream_t)stream;
-  CUtensorMap tmQ, tmK, tmV, tmdO;
+  CUtensorMap tmQ, tmK, tmV, tmdO, tmDQ;
   int rc;
   if ((rc = make_tmap_2d(&tmQ, q, 2, (uint64_t)(H * HD), (uint64_t)(B * Tq), (uint64_t)ldq * 2, HD, BQ, true))) return rc;
   if ((rc = make_tmap_2d(&tmK, k, 2, (uint64_t)(H * HD), (uint64_t)(B * Tkv), (uint64_t)ldk * 2, HD, BKV, true))) return rc;
   if ((rc = make_tmap_2d(&tmV, v, 2, (uint64_t)(H * HD), (uint64_t)(B * Tkv), (uint64_t)ldv * 2, HD, BKV, true))) return rc;
   if ((rc = make_tmap_2d(&tmdO, dout, 2, (uint64_t)(H * HD), (uint64_t)(B * Tq), (uint64_t)lddo * 2, HD, BQ, true))) return rc;
+  if ((rc = make_tmap_2d(&tmDQ, dq_accum, 4, (uint64_t)(H * HD), (uint64_t)(B * Tq), (uint64_t)(H * HD) * 4, 32, BQ, true))) return rc;
 
   const int64_t n_items = B * Tq * H;
   attention_delta_kernel<<<(unsigned)ceil_div(n_items * 8, 256), 256, 0, st>>>((const bf16*)o, (const bf16*)dout, delta, ldo, lddo,
@@ -407,7 +425,7 @@ extern "C" int oasr_attention_bwd(const void* q, int64_t ldq, const void* k, int
     attr_set = true;
   }
   dim3 grid((unsigned)ceil_div(Tkv, BKV), (unsigned)H, (unsigned)B);
-  attention_bwd_kernel<<<grid, 384, BWD_SMEM, st>>>(tmQ, tmK, tmV, tmdO, p);
+  attention_bwd_kernel<<<grid, 384, BWD_SMEM, st>>>(tmQ, tmK, tmV, tmdO, tmDQ, p);
   OASR_LAUNCH_CHECK();
   const int64_t rows = B * Tq;
   int64_t blocks = ceil_div(rows * (H * HD / 8), 256);

@@ -16,6 +16,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--variant", default="medium")
     ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--layers", type=int, default=0, help="truncate encoder/decoder depth (for ncu captures)")
+    ap.add_argument("--no-profiler", action="store_true", help="just run the steps (when wrapped in ncu)")
     args = ap.parse_args()
     import olmoasr_b200 as ob
     from olmoasr_b200 import synthetic as synth
@@ -24,8 +26,12 @@ def main():
 
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
+    dims = ob.VARIANT_TO_DIMS[args.variant]
+    if args.layers:
+        from dataclasses import replace
+        dims = replace(dims, n_audio_layer=args.layers, n_text_layer=args.layers)
     with torch.device(dev):
-        model = OLMoASR(ob.VARIANT_TO_DIMS[args.variant])
+        model = OLMoASR(dims)
     opt = FusedAdamW(model.parameters())
     B = args.batch
     wav = synth.waveforms(B, int16=True).to(dev)
@@ -42,6 +48,10 @@ def main():
     for _ in range(2):
         step()
     torch.cuda.synchronize()
+    if args.no_profiler:
+        step()
+        torch.cuda.synchronize()
+        return
     from torch.profiler import ProfilerActivity, profile
 
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
