@@ -24,6 +24,8 @@
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 
+#include <type_traits>
+
 namespace oasr {
 namespace {
 
@@ -256,26 +258,34 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const float neg = (m == -INFINITY) ? 0.f : -m * c;
       const float2 c2 = make_float2(c, c), n2 = make_float2(neg, neg);
       float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
+      // POLY: odd pairs go through the FMA-pipe polynomial, even pairs through MUFU.EX2 (the two pipes run side by
+      // side).  Masked tiles keep MUFU for every element so that -inf maps to exactly 0.
+      auto emit_p = [&](auto poly_tag) {
+        constexpr bool POLY = decltype(poly_tag)::value;
 #pragma unroll
-      for (int cc = 0; cc < BKV / 32; ++cc) {
-        const uint32_t half_base = sPt + (cc >> 1) * (P_BYTES / 2) + r * 128;
+        for (int cc = 0; cc < BKV / 32; ++cc) {
+          const uint32_t half_base = sPt + (cc >> 1) * (P_BYTES / 2) + r * 128;
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          uint32_t w[4];
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint32_t w[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int i = cc * 32 + q4 * 8 + e * 2;
-            const float2 x = __ffma2_rn(make_float2(v[i], v[i + 1]), c2, n2);
-            const float2 pe = make_float2(fast_exp2(x.x), fast_exp2(x.y));
-            if (e & 1) sum_b = __fadd2_rn(sum_b, pe); else sum_a = __fadd2_rn(sum_a, pe);
-            w[e] = pack_bf16x2(pe.x, pe.y);
+            for (int e = 0; e < 4; ++e) {
+              const int i = cc * 32 + q4 * 8 + e * 2;
+              const float2 x = __ffma2_rn(make_float2(v[i], v[i + 1]), c2, n2);
+              float2 pe;
+              if (POLY && (e & 1)) pe = exp2_poly2(x);
+              else pe = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+              if (e & 1) sum_b = __fadd2_rn(sum_b, pe); else sum_a = __fadd2_rn(sum_a, pe);
+              w[e] = pack_bf16x2(pe.x, pe.y);
+            }
+            const int chunk = (cc & 1) * 4 + q4;       // 16-byte chunk index within the 128-byte row
+            const uint32_t addr = half_base + ((chunk ^ (r & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                         : "memory");
           }
-          const int chunk = (cc & 1) * 4 + q4;       // 16-byte chunk index within the 128-byte row
-          const uint32_t addr = half_base + ((chunk ^ (r & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
-                       : "memory");
         }
-      }
+      };
+      if (limit >= BKV) emit_p(std::true_type{}); else emit_p(std::false_type{});
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
       __syncwarp();

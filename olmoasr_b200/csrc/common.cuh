@@ -77,6 +77,27 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// 2^x for two values on the FMA / ALU pipes (no MUFU): round-to-nearest split x = j + f, f in [-0.5, 0.5], degree-4
+// polynomial for 2^f (rel. error ~4e-5, far below the bf16 rounding of the consumer), exponent patched with an integer
+// add.  The attention kernels send half of their exponentials here: MUFU.EX2 (16 lanes/clk/SM) is their bottleneck
+// while the FMA pipe (128 lanes/clk/SM) idles.  Inputs below -126 flush to ~1e-38.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -126.0f);
+  x.y = fmaxf(x.y, -126.0f);
+  const float2 magic = make_float2(12582912.0f, 12582912.0f);        // 1.5 * 2^23: low mantissa bits = round(x)
+  const float2 t = __fadd2_rn(x, magic);
+  const float2 jf = __fadd2_rn(t, make_float2(-12582912.0f, -12582912.0f));
+  const float2 f = __fadd2_rn(x, make_float2(-jf.x, -jf.y));
+  float2 pl = __ffma2_rn(f, make_float2(0.0096181291f, 0.0096181291f), make_float2(0.0555041087f, 0.0555041087f));
+  pl = __ffma2_rn(pl, f, make_float2(0.2402265070f, 0.2402265070f));
+  pl = __ffma2_rn(pl, f, make_float2(0.6931471806f, 0.6931471806f));
+  pl = __ffma2_rn(pl, f, make_float2(1.0f, 1.0f));
+  float2 r;
+  r.x = __int_as_float(__float_as_int(pl.x) + (__float_as_int(t.x) << 23));
+  r.y = __int_as_float(__float_as_int(pl.y) + (__float_as_int(t.y) << 23));
+  return r;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
