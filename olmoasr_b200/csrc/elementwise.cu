@@ -176,32 +176,48 @@ __global__ void gelu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restr
 }
 
 // ------------------------------------------------------------------ bias gradient: db[n] += sum_m dy[m,n]
-// Block = 32 x 8 threads, tile = 64 columns (2 per thread-x via bf16x2) x a slab of rows.
+// Block = 32 x 8 threads; tile = 256 columns (8 per thread, one 16-byte load) x a slab of rows.
 __global__ void __launch_bounds__(256)
 colsum_kernel(const bf16* __restrict__ dy, float* __restrict__ db, int64_t M, int N, int64_t ld, int rows_per_block) {
-  __shared__ float red[8][64];
-  const int col = blockIdx.x * 64 + threadIdx.x * 2;
+  __shared__ float red[8][256 + 8];
+  const int col = blockIdx.x * 256 + threadIdx.x * 8;
   const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_block;
   const int64_t r1 = min(M, r0 + rows_per_block);
-  float s0 = 0.f, s1 = 0.f;
-  if (col + 1 < N) {
-    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
-      const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dy + r * ld + col));
-      s0 += v.x; s1 += v.y;
-    }
-  } else if (col < N) {
-    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) s0 += __bfloat162float(dy[r * ld + col]);
-  }
-  red[threadIdx.y][threadIdx.x * 2] = s0;
-  red[threadIdx.y][threadIdx.x * 2 + 1] = s1;
-  __syncthreads();
-  if (threadIdx.y == 0) {
-    float a = 0.f, b = 0.f;
+  float s[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { a += red[j][threadIdx.x * 2]; b += red[j][threadIdx.x * 2 + 1]; }
-    if (col < N) atomicAdd(db + col, a);
-    if (col + 1 < N) atomicAdd(db + col + 1, b);
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+  if (col + 8 <= N && (ld & 7) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0) {
+    int64_t r = r0 + threadIdx.y;
+    for (; r + 8 < r1; r += 16) {  // two independent 16-byte loads in flight per thread
+      const uint4 a = *reinterpret_cast<const uint4*>(dy + r * ld + col);
+      const uint4 b = *reinterpret_cast<const uint4*>(dy + (r + 8) * ld + col);
+      const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 p = unpack_bf16x2(av[j]), q = unpack_bf16x2(bv[j]);
+        s[2 * j] += p.x + q.x; s[2 * j + 1] += p.y + q.y;
+      }
+    }
+    for (; r < r1; r += 8) {
+      const uint4 a = *reinterpret_cast<const uint4*>(dy + r * ld + col);
+      const uint32_t av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float2 p = unpack_bf16x2(av[j]); s[2 * j] += p.x; s[2 * j + 1] += p.y; }
+    }
+  } else {
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (col + j < N) s[j] += __bfloat162float(dy[r * ld + col + j]);
   }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.y][threadIdx.x * 8 + j] = s[j];
+  __syncthreads();
+  const int t = threadIdx.y * 32 + threadIdx.x;  // 256 threads -> 256 columns
+  float a = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a += red[j][t];
+  if (blockIdx.x * 256 + t < N) atomicAdd(db + blockIdx.x * 256 + t, a);
 }
 
 }  // namespace
@@ -295,8 +311,8 @@ extern "C" int oasr_gelu_bwd(const void* dy, const void* pre, void* out, int64_t
 
 extern "C" int oasr_colsum_bf16(const void* dy, float* db, int64_t M, int64_t N, int64_t ld, void* stream) {
   OASR_REQUIRE(M > 0 && N > 0 && (ld & 1) == 0, "colsum: bad shape");
-  const int col_tiles = (int)ceil_div(N, 64);
-  int row_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(M, 64), (num_sms() * 8) / col_tiles + 1));
+  const int col_tiles = (int)ceil_div(N, 256);
+  int row_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(M, 64), (num_sms() * 6) / col_tiles + 1));
   const int rows_per_block = (int)ceil_div(M, row_blocks);
   row_blocks = (int)ceil_div(M, rows_per_block);
   colsum_kernel<<<dim3(col_tiles, row_blocks), dim3(32, 8), 0, (cudaStream_t)stream>>>((const bf16*)dy, db, M, (int)N, ld, rows_per_block);

@@ -9,9 +9,12 @@
 //   warp 2       TMEM allocator / deallocator
 //   warps 4..11  epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 (one output row per thread) and the column
 //                half (w-4)/4 of the tile
-// CLUSTER = 2: two CTAs that share an N tile (consecutive M tiles) form a cluster; each loads half of the B tile and
-// TMA-multicasts it to both, which halves the L2 -> SM operand traffic of B (the 128 x 256 tile is otherwise
-// L2-bandwidth bound: 85 FLOP/B against ~12 TB/s).  Stage release is a multicast tcgen05.commit to both CTAs.
+// CLUSTER = 2: two CTAs (an SM pair) compute a 256 x BN tile with ONE tcgen05.mma.cta_group::2 stream issued by the
+// leader CTA: each CTA holds its 128 rows of A and its BN/2 rows of B in its own shared memory, so per flop the
+// tensor core reads half as much smem and TMA writes half as much (the 1-CTA 128 x 256 tile needs 96 B/clk of operand
+// reads plus 96 B/clk of TMA fills against a 128 B/clk shared-memory port; measured 1.30 vs cuBLAS 1.64 PFLOP/s).
+// Both CTAs' TMA loads signal the leader's full barrier; the leader's commits are multicast to both CTAs' empty and
+// accumulator-full barriers; every epilogue warp of the pair arrives on the leader's accumulator-empty barrier.
 //
 // Tile = 128 x BN, BK = 64 bf16 (= one 128-byte swizzle row).  Both operand majors are supported
 // through the UMMA descriptors, so dgrad (B MN-major) and wgrad (A and B MN-major) need no
@@ -44,11 +47,11 @@ struct GemmParams {
   int raster_m;  // 1: consecutive tiles walk M first (B tile stays hot in L2) -- used when B is the larger operand
 };
 
-template <int BN>
+template <int BN, int CLUSTER = 1>
 struct Cfg {
-  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int B_STAGE_BYTES = (BN / CLUSTER) * BK * 2;   // per CTA
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + manual 1 KB alignment slack
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator buffers
 };
@@ -108,7 +111,7 @@ template <int BN, int A_MN, int B_MN, int CLUSTER>
 __global__ void __launch_bounds__(384, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CLUSTER>;
   constexpr int STAGES = C::STAGES;
 
   extern __shared__ uint8_t smem_raw[];
@@ -130,21 +133,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bar_full[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bar_empty[s]), CLUSTER);  // every CTA of the cluster releases the slot
+      ptx::mbar_init(ptx::smem_u32(&bar_empty[s]), 1);
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bar_tmem_full[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bar_tmem_empty[s]), 8);  // one arrive per epilogue warp
+      ptx::mbar_init(ptx::smem_u32(&bar_tmem_empty[s]), 8 * CLUSTER);  // one arrive per epilogue warp of the pair
     }
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc<C::TMEM_COLS>(ptx::smem_u32(&tmem_base_slot));
-    ptx::tmem_relinquish();
+    if (CLUSTER == 1) {
+      ptx::tmem_alloc<C::TMEM_COLS>(ptx::smem_u32(&tmem_base_slot));
+      ptx::tmem_relinquish();
+    } else {  // the same warp of both CTAs allocates the pair's columns
+      ptx::tmem_alloc2<C::TMEM_COLS>(ptx::smem_u32(&tmem_base_slot));
+      ptx::tmem_relinquish2();
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (CLUSTER > 1) ptx::cluster_sync();  // peer barriers are initialised before any multicast / remote arrive
+  if (CLUSTER > 1) ptx::cluster_sync();  // peer barriers are initialised before any remote signal
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
@@ -168,18 +176,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int kb1 = min(kb0 + p.kblocks_per_split, p.kblocks_total);
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(ptx::smem_u32(&bar_empty[stage]), phase ^ 1);
-          const uint32_t full = ptx::smem_u32(&bar_full[stage]);
-          ptx::mbar_arrive_expect_tx(full, C::STAGE_BYTES);
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
           const uint32_t sb = sa + A_STAGE_BYTES;
-          if (A_MN) {
-#pragma unroll
-            for (int i = 0; i < BM / 64; ++i)
-              ptx::tma_load_2d(sa + i * (BK * 128), &tmA, full, m_blk * BM + i * 64, kb * BK);
-          } else {
-            ptx::tma_load_2d(sa, &tmA, full, kb * BK, m_blk * BM);
-          }
           if (CLUSTER == 1) {
+            const uint32_t full = ptx::smem_u32(&bar_full[stage]);
+            ptx::mbar_arrive_expect_tx(full, C::STAGE_BYTES);
+            if (A_MN) {
+#pragma unroll
+              for (int i = 0; i < BM / 64; ++i)
+                ptx::tma_load_2d(sa + i * (BK * 128), &tmA, full, m_blk * BM + i * 64, kb * BK);
+            } else {
+              ptx::tma_load_2d(sa, &tmA, full, kb * BK, m_blk * BM);
+            }
             if (B_MN) {
 #pragma unroll
               for (int i = 0; i < BN / 64; ++i)
@@ -188,16 +196,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               ptx::tma_load_2d(sb, &tmB, full, kb * BK, n_blk * BN);
             }
           } else {
-            // this CTA fetches half of the B tile and multicasts it into both CTAs' stage buffers
-            if (B_MN) {
+            // both CTAs fill their own smem; every byte is accounted on the LEADER's full barrier
+            const uint32_t full = ptx::smem_u32(&bar_full[stage]) & ptx::kPeerBitMask;
+            if (cta_rank == 0) ptx::mbar_arrive_expect_tx(full, CLUSTER * C::STAGE_BYTES);
+            if (A_MN) {
 #pragma unroll
-              for (int i = 0; i < BN / 128; ++i) {
-                const int c = cta_rank * (BN / 128) + i;  // 64-column chunk index
-                ptx::tma_load_2d_mc(sb + c * (BK * 128), &tmB, full, n_blk * BN + c * 64, kb * BK, kMask);
-              }
+              for (int i = 0; i < BM / 64; ++i)
+                ptx::tma_load_2d_2sm(sa + i * (BK * 128), &tmA, full, m_blk * BM + i * 64, kb * BK);
             } else {
-              const int r0 = cta_rank * (BN / 2);
-              ptx::tma_load_2d_mc(sb + r0 * 128, &tmB, full, kb * BK, n_blk * BN + r0, kMask);
+              ptx::tma_load_2d_2sm(sa, &tmA, full, kb * BK, m_blk * BM);
+            }
+            if (B_MN) {   // this CTA's BN/2 columns of B: BN/128 chunks of 64
+#pragma unroll
+              for (int i = 0; i < BN / 128; ++i)
+                ptx::tma_load_2d_2sm(sb + i * (BK * 128), &tmB, full, n_blk * BN + (cta_rank * (BN / 128) + i) * 64, kb * BK);
+            } else {      // this CTA's BN/2 rows of B
+              ptx::tma_load_2d_2sm(sb, &tmB, full, kb * BK, n_blk * BN + cta_rank * (BN / 2));
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -205,9 +219,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, A_MN, B_MN);
+    // ===================== MMA issuer (leader CTA only when paired) =====================
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM * CLUSTER, BN, A_MN, B_MN);
       // K-major  : 8-row groups 1024 B apart (SBO); LBO unused for swizzled K-major (CUTLASS sets 1)
       // MN-major : 64-element MN chunks BK*128 B apart (LBO); 8-k groups 1024 B apart (SBO)
       constexpr uint32_t a_lbo = A_MN ? BK * 128 : 16, a_sbo = 1024;
@@ -234,14 +248,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t ad = ptx::umma_smem_desc_sw128(sa + k * a_kstep, a_lbo, a_sbo);
             const uint64_t bd = ptx::umma_smem_desc_sw128(sb + k * b_kstep, b_lbo, b_sbo);
-            ptx::tc_mma_f16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (CLUSTER == 1) ptx::tc_mma_f16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else ptx::tc_mma2_f16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          // frees the smem slot (in every CTA that multicasts into it) when the MMAs retire
+          // frees the smem slot (in both CTAs of a pair) when the MMAs retire
           if (CLUSTER == 1) ptx::tc_commit(ptx::smem_u32(&bar_empty[stage]));
-          else ptx::tc_commit_mc(ptx::smem_u32(&bar_empty[stage]), kMask);
+          else ptx::tc_commit2_mc(ptx::smem_u32(&bar_empty[stage]), kMask);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        ptx::tc_commit(ptx::smem_u32(&bar_tmem_full[acc]));  // accumulator complete
+        // accumulator complete (each CTA's epilogue drains its own 128 rows)
+        if (CLUSTER == 1) ptx::tc_commit(ptx::smem_u32(&bar_tmem_full[acc]));
+        else ptx::tc_commit2_mc(ptx::smem_u32(&bar_tmem_full[acc]), kMask);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -358,7 +375,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_tmem_empty[acc]));
+      if (lane == 0) {
+        if (CLUSTER == 1) ptx::mbar_arrive(ptx::smem_u32(&bar_tmem_empty[acc]));
+        else ptx::mbar_arrive_cluster(ptx::smem_u32(&bar_tmem_empty[acc]) & ptx::kPeerBitMask);  // the leader's barrier
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -368,13 +388,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (CLUSTER > 1) ptx::cluster_sync();  // no CTA exits while its peer can still multicast into it
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<C::TMEM_COLS>(tmem_base);
+    if (CLUSTER == 1) ptx::tmem_dealloc<C::TMEM_COLS>(tmem_base);
+    else ptx::tmem_dealloc2<C::TMEM_COLS>(tmem_base);
   }
 }
 
 template <int BN, int A_MN, int B_MN, int CLUSTER>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CLUSTER>;
   auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, CLUSTER>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
@@ -462,7 +483,7 @@ extern "C" int oasr_gemm_bf16(const void* A, int64_t lda, int a_layout, const vo
   if (rc) return rc;
 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  // multicast pairs need >= 2 M tiles and a B tile that splits in two TMA boxes; OASR_GEMM_CLUSTER=1 disables (A/B tests)
+  // CTA pairs need >= 2 M tiles and a B tile that splits in two; OASR_GEMM_CLUSTER=1 selects the 1-CTA kernel (A/B tests)
   static const int env_cluster = [] { const char* e = getenv("OASR_GEMM_CLUSTER"); return e ? atoi(e) : 2; }();
   const bool pair = env_cluster >= 2 && p.tiles_m >= 2 && block_n >= 128;
   switch (block_n) {

@@ -71,7 +71,30 @@ adamw_kernel(const TensorRec* __restrict__ recs, const int2* __restrict__ chunks
   float* v = r.v + start;
   const float step_size = lr / bc1;
   const float decay = 1.f - lr * weight_decay;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  int i0 = 0;
+  if (((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+        reinterpret_cast<uintptr_t>(v)) & 15) == 0) {
+    const int n4 = n & ~3;
+    for (int i = threadIdx.x * 4; i < n4; i += blockDim.x * 4) {   // 16-byte accesses: 7 vector transactions per 4 params
+      float4 pv = *reinterpret_cast<float4*>(p + i);
+      const float4 gv = *reinterpret_cast<const float4*>(g + i);
+      float4 mv = *reinterpret_cast<float4*>(m + i);
+      float4 vv = *reinterpret_cast<float4*>(v + i);
+      float* pp = &pv.x; const float* gp = &gv.x; float* mp = &mv.x; float* vp = &vv.x;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float gi = gp[j] * coef;
+        mp[j] = beta1 * mp[j] + (1.f - beta1) * gi;
+        vp[j] = beta2 * vp[j] + (1.f - beta2) * gi * gi;
+        pp[j] = pp[j] * decay - step_size * (mp[j] / (sqrtf(vp[j]) / bc2_sqrt + eps));
+      }
+      *reinterpret_cast<float4*>(p + i) = pv;
+      *reinterpret_cast<float4*>(m + i) = mv;
+      *reinterpret_cast<float4*>(v + i) = vv;
+    }
+    i0 = n4;
+  }
+  for (int i = i0 + threadIdx.x; i < n; i += blockDim.x) {
     const float gi = g[i] * coef;
     const float mi = beta1 * m[i] + (1.f - beta1) * gi;
     const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
