@@ -260,13 +260,13 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_free));   // S / dP TMEM may be overwritten
-      if (it > 0) drain_dq(it - 1);   // also: dV/dK/dQ MMAs of the previous tile retired => sP / sdS reusable
-
+      // All the exp / dS math happens BEFORE waiting for the previous tile's dV/dK/dQ MMAs (which still read sP / sdS):
+      // the results wait in registers as packed bf16, so the compute warps never idle behind the tensor pipe.
       const float2 c2 = make_float2(c, c), nl2 = make_float2(-lse, -lse), nd2 = make_float2(-dlt, -dlt);
+      uint32_t pp[32], dd[32];   // 64 columns each, packed bf16x2
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         const int cc = chalf * 2 + hh;
-        float pr[32], ds[32];
         const bool full = (cc + 1) * 32 <= limit;
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
@@ -277,13 +277,25 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             if (cc * 32 + i >= limit) pe.x = 0.f;
             if (cc * 32 + i + 1 >= limit) pe.y = 0.f;
           }
-          const float2 dd = __fadd2_rn(make_float2(__uint_as_float(dv[hh * 32 + i]), __uint_as_float(dv[hh * 32 + i + 1])), nd2);
-          const float2 dsv = __fmul2_rn(pe, dd);
-          pr[i] = pe.x; pr[i + 1] = pe.y;
-          ds[i] = dsv.x; ds[i + 1] = dsv.y;
+          const float2 dq2 = __fadd2_rn(make_float2(__uint_as_float(dv[hh * 32 + i]), __uint_as_float(dv[hh * 32 + i + 1])), nd2);
+          const float2 dsv = __fmul2_rn(pe, dq2);
+          pp[hh * 16 + (i >> 1)] = pack_bf16x2(pe.x, pe.y);
+          dd[hh * 16 + (i >> 1)] = pack_bf16x2(dsv.x, dsv.y);
         }
-        store_swizzled_row32(sP, r, cc, pr);
-        store_swizzled_row32(sdS, r, cc, ds);
+      }
+      if (it > 0) drain_dq(it - 1);   // dV/dK/dQ MMAs of the previous tile retired => sP / sdS reusable
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int cc = chalf * 2 + hh;
+        const uint32_t off = (cc >> 1) * (P_BYTES / 2) + r * 128;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const uint32_t a = off + ((((cc & 1) * 4 + q4) ^ (r & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP + a), "r"(pp[hh * 16 + q4 * 4]), "r"(pp[hh * 16 + q4 * 4 + 1]),
+                       "r"(pp[hh * 16 + q4 * 4 + 2]), "r"(pp[hh * 16 + q4 * 4 + 3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdS + a), "r"(dd[hh * 16 + q4 * 4]), "r"(dd[hh * 16 + q4 * 4 + 1]),
+                       "r"(dd[hh * 16 + q4 * 4 + 2]), "r"(dd[hh * 16 + q4 * 4 + 3]) : "memory");
+        }
       }
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();

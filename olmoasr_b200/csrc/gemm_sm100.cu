@@ -273,6 +273,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const bool c_is_f32 = (p.epi == OASR_EPI_F32 || p.epi == OASR_EPI_F32_ATOMIC_ADD);
     const bool vec_c = c_is_f32 ? ((p.ldc & 3) == 0) : ((p.ldc & 7) == 0);
     const bool vec_aux = (p.ldaux & 7) == 0;
+    const bool use_aux = (p.epi == OASR_EPI_BF16_RESIDUAL || p.epi == OASR_EPI_BF16_GELU_BWD);
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       int n_blk, m_blk, split_unused;
       decode_tile(tile, p, tiles_mc, CLUSTER, cta_rank, m_blk, n_blk, split_unused);
@@ -286,11 +287,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");  // epilogue warps only
       }
+      // aux (residual / pre-activation) rows of this thread, fetched before the accumulator is ready so that the
+      // ~1 us global-load latency hides behind the MMAs (it used to be the top stall of the residual epilogue)
+      constexpr int NCH = BN / 64;   // 32-column chunks per epilogue warp (1, 2 or 4)
+      if (use_aux && row_ok) {       // pull this thread's aux bytes towards L2/L1 while the accumulator is still being computed
+#pragma unroll
+        for (int ci = 0; ci < NCH; ++ci) {
+          const int col = n_blk * BN + (chalf * NCH + ci) * 32;
+          if (col < p.N)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const bf16*>(p.aux) + static_cast<int64_t>(row) * p.ldaux + col));
+        }
+      }
       ptx::mbar_wait(ptx::smem_u32(&bar_tmem_full[acc]), acc_phase);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-      for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
+      for (int ci = 0; ci < NCH; ++ci) {
+        const int c = chalf * NCH + ci;
+        const int col_c = n_blk * BN + c * 32;
+        const bool aux_here = use_aux && vec_aux && row_ok && (col_c + 32 <= p.N);
+        uint4 auxc[4];
+        if (aux_here) {   // issued before the TMEM load so both latencies overlap
+          const uint4* ap4 = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.aux) + static_cast<int64_t>(row) * p.ldaux + col_c);
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) auxc[q4] = ap4[q4];
+        }
         uint32_t r[32];
         __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent `continue`
         ptx::tc_ld_32x32b_x32(t_row + c * 32, r);
@@ -315,29 +336,80 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             store_bf16x32(reinterpret_cast<bf16*>(p.C) + off, x, nvalid, vec_c);
             break;
           case OASR_EPI_BF16_GELU: {
-            float g[32];
+            if (vec_c && nvalid == 32) {   // packed path: h = bf16(acc + b), g = bf16(gelu(h)), two elements per op
+              uint32_t hp[16], gp[16];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { x[j] = bf16_round(x[j]); g[j] = gelu_erf(x[j]); }
-            store_bf16x32(reinterpret_cast<bf16*>(p.C) + off, x, nvalid, vec_c);
-            store_bf16x32(reinterpret_cast<bf16*>(p.C2) + off, g, nvalid, vec_c);
+              for (int j = 0; j < 16; ++j) {
+                hp[j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
+                const float2 g2 = gelu_erf2(unpack_bf16x2(hp[j]));
+                gp[j] = pack_bf16x2(g2.x, g2.y);
+              }
+              uint4* d1 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.C) + off);
+              uint4* d2 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.C2) + off);
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4) {
+                d1[q4] = make_uint4(hp[4 * q4], hp[4 * q4 + 1], hp[4 * q4 + 2], hp[4 * q4 + 3]);
+                d2[q4] = make_uint4(gp[4 * q4], gp[4 * q4 + 1], gp[4 * q4 + 2], gp[4 * q4 + 3]);
+              }
+            } else {
+              float g[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) { x[j] = bf16_round(x[j]); g[j] = gelu_erf(x[j]); }
+              store_bf16x32(reinterpret_cast<bf16*>(p.C) + off, x, nvalid, vec_c);
+              store_bf16x32(reinterpret_cast<bf16*>(p.C2) + off, g, nvalid, vec_c);
+            }
             break;
           }
           case OASR_EPI_BF16_RESIDUAL: {
-            float a[32];
-            load_bf16x32(reinterpret_cast<const bf16*>(p.aux) + static_cast<int64_t>(row) * p.ldaux + col,
-                         a, nvalid, vec_aux);
+            if (aux_here && vec_c && nvalid == 32) {   // packed: C = bf16(aux + bf16(acc + b))
+              uint4* d1 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.C) + off);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = a[j] + bf16_round(x[j]);
-            store_bf16x32(reinterpret_cast<bf16*>(p.C) + off, x, nvalid, vec_c);
+              for (int q4 = 0; q4 < 4; ++q4) {
+                const uint32_t aw[4] = {auxc[q4].x, auxc[q4].y, auxc[q4].z, auxc[q4].w};
+                uint32_t ow[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int j = q4 * 8 + e * 2;
+                  const float2 y = unpack_bf16x2(pack_bf16x2(x[j], x[j + 1]));
+                  const float2 o = __fadd2_rn(unpack_bf16x2(aw[e]), y);
+                  ow[e] = pack_bf16x2(o.x, o.y);
+                }
+                d1[q4] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+              }
+            } else {
+              float a[32];
+              load_bf16x32(reinterpret_cast<const bf16*>(p.aux) + static_cast<int64_t>(row) * p.ldaux + col, a, nvalid, vec_aux);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = a[j] + bf16_round(x[j]);
+              store_bf16x32(reinterpret_cast<bf16*>(p.C) + off, x, nvalid, vec_c);
+            }
             break;
           }
           case OASR_EPI_BF16_GELU_BWD: {
-            float a[32];
-            load_bf16x32(reinterpret_cast<const bf16*>(p.aux) + static_cast<int64_t>(row) * p.ldaux + col,
-                         a, nvalid, vec_aux);
+            const bf16* ap = reinterpret_cast<const bf16*>(p.aux) + static_cast<int64_t>(row) * p.ldaux + col;
+            if (aux_here && vec_c && nvalid == 32) {   // packed path on the prefetched pre-activations
+              uint4* d1 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.C) + off);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = bf16_round(x[j]) * gelu_erf_grad(a[j]);
-            store_bf16x32(reinterpret_cast<bf16*>(p.C) + off, x, nvalid, vec_c);
+              for (int q4 = 0; q4 < 4; ++q4) {
+                const uint32_t hw[4] = {auxc[q4].x, auxc[q4].y, auxc[q4].z, auxc[q4].w};
+                uint32_t ow[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int j = q4 * 8 + e * 2;
+                  const float2 dg = unpack_bf16x2(pack_bf16x2(x[j], x[j + 1]));   // bf16(acc): the matmul-backward output
+                  const float2 gr = gelu_erf_grad2(unpack_bf16x2(hw[e]));
+                  const float2 o = __fmul2_rn(dg, gr);
+                  ow[e] = pack_bf16x2(o.x, o.y);
+                }
+                d1[q4] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+              }
+            } else {
+              float a[32];
+              load_bf16x32(ap, a, nvalid, vec_aux);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = bf16_round(x[j]) * gelu_erf_grad(a[j]);
+              store_bf16x32(reinterpret_cast<bf16*>(p.C) + off, x, nvalid, vec_c);
+            }
             break;
           }
           case OASR_EPI_F32: {
