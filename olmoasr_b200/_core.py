@@ -93,9 +93,26 @@ def linear_wgrad(dy: Tensor, x: Tensor, n_valid: Optional[int] = None):
                   epi=K.EPI_F32 if out is None else K.EPI_F32_ATOMIC_ADD, split_k=split, block_n=bn)
 
 
-def bias_grad(dy: Tensor, n: Optional[int] = None) -> Tensor:
+class _ZeroPool:
+    """One zero-fill per backward instead of one per small gradient vector (each fill is a separate ~4 us launch;
+    ~700 of them per step otherwise).  Slices are 64-element aligned so every view stays 256-byte aligned."""
+
+    def __init__(self, n_total: int, device):
+        self.buf = torch.zeros(n_total, device=device, dtype=torch.float32)
+        self.off = 0
+
+    def take(self, n: int) -> Tensor:
+        m = (n + 63) // 64 * 64
+        if self.off + m > self.buf.numel():  # defensive: never hand out overlapping storage
+            return torch.zeros(n, device=self.buf.device, dtype=torch.float32)
+        v = self.buf[self.off:self.off + n]
+        self.off += m
+        return v
+
+
+def bias_grad(dy: Tensor, n: Optional[int] = None, pool: Optional[_ZeroPool] = None) -> Tensor:
     n = dy.shape[1] if n is None else n
-    db = torch.zeros(n, device=dy.device, dtype=torch.float32)
+    db = pool.take(n) if pool is not None else torch.zeros(n, device=dy.device, dtype=torch.float32)
     return K.colsum_(dy, db, n)
 
 
@@ -295,14 +312,15 @@ class _BlockFn(torch.autograd.Function):
         dx3 = dx3.contiguous()
         dev = x.device
         grads: Dict[str, Tensor] = {}
-        z = lambda n: torch.zeros(n, device=dev, dtype=torch.float32)
+        pool = _ZeroPool(32 * d + 4096, dev)   # all bias / LayerNorm gradient vectors of this block (<= 26 d)
+        z = pool.take
 
         # ---- MLP: x3 = x2 + fc2(gelu(fc1(ln(x2))))
         grads["mlp.2.weight"] = linear_wgrad(dx3, g)
-        grads["mlp.2.bias"] = bias_grad(dx3)
+        grads["mlp.2.bias"] = bias_grad(dx3, pool=pool)
         dh = linear_dgrad(dx3, sh["w2"], epi=K.EPI_BF16_GELU_BWD, aux=h)
         grads["mlp.0.weight"] = linear_wgrad(dh, ln2)
-        grads["mlp.0.bias"] = bias_grad(dh)
+        grads["mlp.0.bias"] = bias_grad(dh, pool=pool)
         dln2 = linear_dgrad(dh, sh["w1"])
         grads["mlp_ln.weight"], grads["mlp_ln.bias"] = z(d), z(d)
         dx2 = K.layernorm_bwd(dln2, x2, blk.mlp_ln.weight, mean2, rstd2, grads["mlp_ln.weight"], grads["mlp_ln.bias"],
@@ -311,16 +329,16 @@ class _BlockFn(torch.autograd.Function):
         if cross:
             # ---- cross attention: x2 = x1 + out(attn(q(ln(x1)), kv(xa)))
             grads["cross_attn.out.weight"] = linear_wgrad(dx2, co)
-            grads["cross_attn.out.bias"] = bias_grad(dx2)
+            grads["cross_attn.out.bias"] = bias_grad(dx2, pool=pool)
             dco = linear_dgrad(dx2, sh["wco"])
             dqc = torch.empty_like(qc)
             dkvc = torch.empty_like(kvc)
             K.attention_bwd(qc, kvc[:, :d], kvc[:, d:], co, dco, lsec, B, H, T, Ta, dq=dqc, dk=dkvc[:, :d], dv=dkvc[:, d:])
             grads["cross_attn.query.weight"] = linear_wgrad(dqc, lnc)
-            grads["cross_attn.query.bias"] = bias_grad(dqc)
+            grads["cross_attn.query.bias"] = bias_grad(dqc, pool=pool)
             dwkv = linear_wgrad(dkvc, xa)
             grads["cross_attn.key.weight"], grads["cross_attn.value.weight"] = dwkv[:d], dwkv[d:]
-            grads["cross_attn.value.bias"] = bias_grad(dkvc)[d:]
+            grads["cross_attn.value.bias"] = bias_grad(dkvc, pool=pool)[d:]
             dxa = linear_dgrad(dkvc, sh["wckv"])
             dlnc = linear_dgrad(dqc, sh["wcq"])
             grads["cross_attn_ln.weight"], grads["cross_attn_ln.bias"] = z(d), z(d)
@@ -330,14 +348,14 @@ class _BlockFn(torch.autograd.Function):
             dx1 = dx2
         # ---- self attention: x1 = x + out(attn(qkv(ln(x))))
         grads["attn.out.weight"] = linear_wgrad(dx1, ao)
-        grads["attn.out.bias"] = bias_grad(dx1)
+        grads["attn.out.bias"] = bias_grad(dx1, pool=pool)
         dao = linear_dgrad(dx1, sh["wo"])
         dqkv = torch.empty_like(qkv)
         K.attention_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], ao, dao, lse, B, H, T, T, causal=causal, kv_len=kv_len,
                         dq=dqkv[:, :d], dk=dqkv[:, d:2 * d], dv=dqkv[:, 2 * d:])
         dw = linear_wgrad(dqkv, ln1)
         grads["attn.query.weight"], grads["attn.key.weight"], grads["attn.value.weight"] = dw[:d], dw[d:2 * d], dw[2 * d:]
-        db = bias_grad(dqkv)
+        db = bias_grad(dqkv, pool=pool)
         grads["attn.query.bias"], grads["attn.value.bias"] = db[:d], db[2 * d:]
         dln1 = linear_dgrad(dqkv, sh["wqkv"])
         grads["attn_ln.weight"], grads["attn_ln.bias"] = z(d), z(d)

@@ -271,8 +271,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           const float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[hh * 32 + i]), __uint_as_float(sv[hh * 32 + i + 1])), c2, nl2);
-          // alternate pairs between MUFU.EX2 and the FMA-pipe polynomial (see exp2_poly2)
-          float2 pe = (i & 2) ? exp2_poly2(x) : make_float2(fast_exp2(x.x), fast_exp2(x.y));
+          // MUFU.EX2 for every element: ncu shows the XU pipe at 8 % while issue slots are the scarce resource here,
+          // and the FMA-pipe polynomial (exp2_poly2) costs ~6 issue slots per element against 1
+          float2 pe = make_float2(fast_exp2(x.x), fast_exp2(x.y));
           if (!full) {
             if (cc * 32 + i >= limit) pe.x = 0.f;
             if (cc * 32 + i + 1 >= limit) pe.y = 0.f;

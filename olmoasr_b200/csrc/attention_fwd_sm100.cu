@@ -285,7 +285,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           }
         }
       };
-      if (limit >= BKV) emit_p(std::true_type{}); else emit_p(std::false_type{});
+      // ncu (profiles/r01_ncu_kernel_metrics.txt): XU pipe 30 %, issue slots 50 % busy with two softmax warps per
+      // scheduler -- issue slots, not MUFU, are scarce, so the polynomial path (6 slots per element) stays off
+      emit_p(std::false_type{});
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
       __syncwarp();
