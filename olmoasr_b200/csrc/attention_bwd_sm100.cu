@@ -19,6 +19,8 @@
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 
+#include <type_traits>
+
 namespace oasr {
 namespace {
 
@@ -34,7 +36,7 @@ constexpr int BWD_TILES = 2 * TILE_BYTES + Q_STAGES * 2 * TILE_BYTES + 2 * P_BYT
 constexpr int BWD_SMEM = BWD_TILES + 256;
 constexpr int TMEM_COLS = 512;
 constexpr int S_COL = 0, DP_COL = 128, DV_COL = 256, DK_COL = 320, DQ_COL = 384;
-constexpr int COMPUTE_REGS = 192, CONTROL_REGS = 120;   // 8 * 192 + 4 * 120 == 12 * 168 (no spills in either role)
+constexpr int COMPUTE_REGS = 184, CONTROL_REGS = 136;   // 8 * 184 + 4 * 136 == 12 * 168
 
 struct BwdParams {
   const float* lse;   // (B,H,Tq) log2 domain
@@ -264,26 +266,29 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       // the results wait in registers as packed bf16, so the compute warps never idle behind the tensor pipe.
       const float2 c2 = make_float2(c, c), nl2 = make_float2(-lse, -lse), nd2 = make_float2(-dlt, -dlt);
       uint32_t pp[32], dd[32];   // 64 columns each, packed bf16x2
+      // MASKED is decided per warp (warp-uniform branch): interior tiles run without any per-element predicate code
+      auto p_ds = [&](auto masked_tag) {
+        constexpr bool MASKED = decltype(masked_tag)::value;
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int cc = chalf * 2 + hh;
-        const bool full = (cc + 1) * 32 <= limit;
+        for (int hh = 0; hh < 2; ++hh) {
+          const int cc = chalf * 2 + hh;
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[hh * 32 + i]), __uint_as_float(sv[hh * 32 + i + 1])), c2, nl2);
-          // MUFU.EX2 for every element: ncu shows the XU pipe at 8 % while issue slots are the scarce resource here,
-          // and the FMA-pipe polynomial (exp2_poly2) costs ~6 issue slots per element against 1
-          float2 pe = make_float2(fast_exp2(x.x), fast_exp2(x.y));
-          if (!full) {
-            if (cc * 32 + i >= limit) pe.x = 0.f;
-            if (cc * 32 + i + 1 >= limit) pe.y = 0.f;
+          for (int i = 0; i < 32; i += 2) {
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[hh * 32 + i]), __uint_as_float(sv[hh * 32 + i + 1])), c2, nl2);
+            // MUFU.EX2 for every element: ncu shows the XU pipe at 8 % while issue slots are the scarce resource here
+            float2 pe = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+            if (MASKED) {
+              if (cc * 32 + i >= limit) pe.x = 0.f;
+              if (cc * 32 + i + 1 >= limit) pe.y = 0.f;
+            }
+            const float2 dq2 = __fadd2_rn(make_float2(__uint_as_float(dv[hh * 32 + i]), __uint_as_float(dv[hh * 32 + i + 1])), nd2);
+            const float2 dsv = __fmul2_rn(pe, dq2);
+            pp[hh * 16 + (i >> 1)] = pack_bf16x2(pe.x, pe.y);
+            dd[hh * 16 + (i >> 1)] = pack_bf16x2(dsv.x, dsv.y);
           }
-          const float2 dq2 = __fadd2_rn(make_float2(__uint_as_float(dv[hh * 32 + i]), __uint_as_float(dv[hh * 32 + i + 1])), nd2);
-          const float2 dsv = __fmul2_rn(pe, dq2);
-          pp[hh * 16 + (i >> 1)] = pack_bf16x2(pe.x, pe.y);
-          dd[hh * 16 + (i >> 1)] = pack_bf16x2(dsv.x, dsv.y);
         }
-      }
+      };
+      if (__all_sync(0xffffffffu, limit >= (chalf + 1) * 64)) p_ds(std::false_type{}); else p_ds(std::true_type{});
       if (it > 0) drain_dq(it - 1);   // dV/dK/dQ MMAs of the previous tile retired => sP / sdS reusable
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
