@@ -148,22 +148,38 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         ptx::tma_load_2d(sQ0 + s * 2 * TILE_BYTES + TILE_BYTES, &tmdO, full, h * HD, qrow);
         if (++s == Q_STAGES) { s = 0; ph ^= 1; }
       }
-    } else if (warp == 9 && lane == 0 && n_iter > 0) {
-      // ------------------------------ MMA issuer ------------------------------
+    } else if (warp == 9 && n_iter > 0) {
+      // ------------------------------ MMA issuer (whole warp convergent; elect.sync picks the issuing lane) ------------------------------
       constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, 128, 0, 0);    // S, dP
       constexpr uint32_t idesc_kv = ptx::umma_idesc_bf16(128, 64, 1, 1);    // dV, dK
       constexpr uint32_t idesc_dq = ptx::umma_idesc_bf16(128, 64, 0, 1);    // dQ
+      // descriptor bases: K-major operands (LBO unused = 16, SBO 1024); MN-major A from sP / sdS (LBO = half tile),
+      // MN-major B from the [rows][64] tiles (single 64-wide chunk: LBO unused)
+      uint32_t hi_k, hi_mnA, hi_mnB, u;
+      uint32_t kK_lo, vK_lo, q_lo0, do_lo0, pT_lo, dsT_lo, dsK_lo, doB_lo0, qB_lo0, kB_lo;
+      ptx::umma_desc_sw128_lh(sK, 16, 1024, kK_lo, hi_k);
+      ptx::umma_desc_sw128_lh(sV, 16, 1024, vK_lo, u);
+      ptx::umma_desc_sw128_lh(sQ0, 16, 1024, q_lo0, u);
+      ptx::umma_desc_sw128_lh(sQ0 + TILE_BYTES, 16, 1024, do_lo0, u);
+      ptx::umma_desc_sw128_lh(sP, P_BYTES / 2, 1024, pT_lo, hi_mnA);
+      ptx::umma_desc_sw128_lh(sdS, P_BYTES / 2, 1024, dsT_lo, u);
+      ptx::umma_desc_sw128_lh(sdS, 16, 1024, dsK_lo, u);
+      ptx::umma_desc_sw128_lh(sQ0 + TILE_BYTES, BQ * 128, 1024, doB_lo0, hi_mnB);
+      ptx::umma_desc_sw128_lh(sQ0, BQ * 128, 1024, qB_lo0, u);
+      ptx::umma_desc_sw128_lh(sK, BKV * 128, 1024, kB_lo, u);
+      constexpr uint32_t STAGE_LO = (2 * TILE_BYTES) >> 4;
       auto issue_s_dp = [&](int stage) {
-        const uint32_t sQ = sQ0 + stage * 2 * TILE_BYTES, sdO = sQ + TILE_BYTES;
+        const uint32_t ql = q_lo0 + stage * STAGE_LO, dol = do_lo0 + stage * STAGE_LO;
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          ptx::tc_mma_f16(tmem + S_COL, ptx::umma_smem_desc_sw128(sQ + k * 32, 16, 1024),
-                          ptx::umma_smem_desc_sw128(sK + k * 32, 16, 1024), idesc_s, k > 0);
+          for (int k = 0; k < HD / 16; ++k)
+            ptx::tc_mma_f16_lh(tmem + S_COL, ql + k * 2, hi_k, kK_lo + k * 2, hi_k, idesc_s, k > 0);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          ptx::tc_mma_f16(tmem + DP_COL, ptx::umma_smem_desc_sw128(sdO + k * 32, 16, 1024),
-                          ptx::umma_smem_desc_sw128(sV + k * 32, 16, 1024), idesc_s, k > 0);
-        ptx::tc_commit(ptx::smem_u32(&bar_sdp));
+          for (int k = 0; k < HD / 16; ++k)
+            ptx::tc_mma_f16_lh(tmem + DP_COL, dol + k * 2, hi_k, vK_lo + k * 2, hi_k, idesc_s, k > 0);
+          ptx::tc_commit(ptx::smem_u32(&bar_sdp));
+        }
+        __syncwarp();
       };
       ptx::mbar_wait(ptx::smem_u32(&bar_kv), 0);
       ptx::mbar_wait(ptx::smem_u32(&bar_q_full[0]), 0);
@@ -181,28 +197,28 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           ptx::tc_fence_after();
           issue_s_dp(st_n);
         }
-        const uint32_t sQ = sQ0 + st * 2 * TILE_BYTES, sdO = sQ + TILE_BYTES;
+        const uint32_t dob = doB_lo0 + st * STAGE_LO, qb = qB_lo0 + st * STAGE_LO;
         ptx::mbar_wait(ptx::smem_u32(&bar_pds), it & 1);  // P, dS in smem; dQ TMEM drained
         ptx::tc_fence_after();
+        if (ptx::elect_one()) {
 #pragma unroll
         for (int k = 0; k < BQ / 16; ++k) {  // reduction over the 128 query rows, 16 at a time
-          const uint64_t a_p = ptx::umma_smem_desc_sw128(sP + k * 2048, P_BYTES / 2, 1024);     // P^T  (MN-major A)
-          const uint64_t a_ds = ptx::umma_smem_desc_sw128(sdS + k * 2048, P_BYTES / 2, 1024);   // dS^T (MN-major A)
-          const uint64_t b_do = ptx::umma_smem_desc_sw128(sdO + k * 2048, BQ * 128, 1024);      // dO   (MN-major B)
-          const uint64_t b_q = ptx::umma_smem_desc_sw128(sQ + k * 2048, BQ * 128, 1024);        // Q    (MN-major B)
-          ptx::tc_mma_f16(tmem + DV_COL, a_p, b_do, idesc_kv, (it > 0 || k > 0) ? 1u : 0u);
-          ptx::tc_mma_f16(tmem + DK_COL, a_ds, b_q, idesc_kv, (it > 0 || k > 0) ? 1u : 0u);
+          ptx::tc_mma_f16_lh(tmem + DV_COL, pT_lo + k * (2048 >> 4), hi_mnA, dob + k * (2048 >> 4), hi_mnB, idesc_kv,
+                             (it > 0 || k > 0) ? 1u : 0u);
+          ptx::tc_mma_f16_lh(tmem + DK_COL, dsT_lo + k * (2048 >> 4), hi_mnA, qb + k * (2048 >> 4), hi_mnB, idesc_kv,
+                             (it > 0 || k > 0) ? 1u : 0u);
         }
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k)   // dQ_i = dS K : reduction over the 128 keys
-          ptx::tc_mma_f16(tmem + DQ_COL,
-                          ptx::umma_smem_desc_sw128(sdS + (k >> 2) * (P_BYTES / 2) + (k & 3) * 32, 16, 1024),
-                          ptx::umma_smem_desc_sw128(sK + k * 2048, BKV * 128, 1024), idesc_dq, k > 0);
+          ptx::tc_mma_f16_lh(tmem + DQ_COL, dsK_lo + (k >> 2) * ((P_BYTES / 2) >> 4) + (k & 3) * 2, hi_k,
+                             kB_lo + k * (2048 >> 4), hi_mnB, idesc_dq, k > 0);
         ptx::tc_commit(ptx::smem_u32(&bar_dq));
         ptx::tc_commit(ptx::smem_u32(&bar_q_empty[st]));
+        if (it + 1 == n_iter) ptx::tc_commit(ptx::smem_u32(&bar_done));
+        }
+        __syncwarp();
         st = st_n; st_ph = ph_n;
       }
-      ptx::tc_commit(ptx::smem_u32(&bar_done));
     }
   } else {
     // ----------------------------- compute warps -----------------------------

@@ -131,28 +131,38 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         ptx::tma_load_2d(sK0 + s * 2 * TILE_BYTES + TILE_BYTES, &tmV, full, h * HD, krow);
         if (++s == KV_STAGES) { s = 0; ph ^= 1; }
       }
-    } else if (warp == 9 && lane == 0 && n_max > 0) {
-      // ------------------------------ MMA issuer ------------------------------
+    } else if (warp == 9 && n_max > 0) {
+      // ------------------------------ MMA issuer (whole warp convergent; elect.sync picks the issuing lane) ------------------------------
       constexpr uint32_t idesc_qk = ptx::umma_idesc_bf16(BQ, BKV, 0, 0);
       constexpr uint32_t idesc_pv = ptx::umma_idesc_bf16(BQ, HD, 0, 1);
+      uint32_t q_lo[2], p_lo[2], k_lo0, v_lo0, hi_k, hi_v, unused;
+      ptx::umma_desc_sw128_lh(sQ, 16, 1024, q_lo[0], hi_k);
+      ptx::umma_desc_sw128_lh(sQ + TILE_BYTES, 16, 1024, q_lo[1], unused);
+      ptx::umma_desc_sw128_lh(sP, 16, 1024, p_lo[0], unused);
+      ptx::umma_desc_sw128_lh(sP + P_BYTES, 16, 1024, p_lo[1], unused);
+      ptx::umma_desc_sw128_lh(sK0, 16, 1024, k_lo0, unused);
+      ptx::umma_desc_sw128_lh(sK0 + TILE_BYTES, BKV * 128, 1024, v_lo0, hi_v);
+      constexpr uint32_t STAGE_LO = (2 * TILE_BYTES) >> 4;
       auto issue_qk = [&](int t, int stage) {
-        const uint32_t sK = sK0 + stage * 2 * TILE_BYTES;
-        const uint32_t sQt = sQ + t * TILE_BYTES;
+        const uint32_t klo = k_lo0 + stage * STAGE_LO;
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          ptx::tc_mma_f16(tmem + S_COL + t * BKV, ptx::umma_smem_desc_sw128(sQt + k * 32, 16, 1024),
-                          ptx::umma_smem_desc_sw128(sK + k * 32, 16, 1024), idesc_qk, k > 0);
-        ptx::tc_commit(ptx::smem_u32(&bar_s[t]));
+          for (int k = 0; k < HD / 16; ++k)
+            ptx::tc_mma_f16_lh(tmem + S_COL + t * BKV, q_lo[t] + k * 2, hi_k, klo + k * 2, hi_k, idesc_qk, k > 0);
+          ptx::tc_commit(ptx::smem_u32(&bar_s[t]));
+        }
+        __syncwarp();
       };
       auto issue_pv = [&](int t, int stage, int j) {
-        const uint32_t sV = sK0 + stage * 2 * TILE_BYTES + TILE_BYTES;
-        const uint32_t sPt = sP + t * P_BYTES;
+        const uint32_t vlo = v_lo0 + stage * STAGE_LO;
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < BKV / 16; ++k)
-          ptx::tc_mma_f16(tmem + O_COL + t * HD,
-                          ptx::umma_smem_desc_sw128(sPt + (k >> 2) * (P_BYTES / 2) + (k & 3) * 32, 16, 1024),
-                          ptx::umma_smem_desc_sw128(sV + k * 2048, BKV * 128, 1024), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
-        ptx::tc_commit(ptx::smem_u32(&bar_pv[t]));
+          for (int k = 0; k < BKV / 16; ++k)
+            ptx::tc_mma_f16_lh(tmem + O_COL + t * HD, p_lo[t] + (k >> 2) * ((P_BYTES / 2) >> 4) + (k & 3) * 2, hi_k,
+                               vlo + k * (2048 >> 4), hi_v, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+          ptx::tc_commit(ptx::smem_u32(&bar_pv[t]));
+        }
+        __syncwarp();
       };
       ptx::mbar_wait(ptx::smem_u32(&bar_q), 0);
       ptx::mbar_wait(ptx::smem_u32(&bar_kv_full[0]), 0);
@@ -187,7 +197,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             issue_pv(t, st, j);
           }
         }
-        ptx::tc_commit(ptx::smem_u32(&bar_kv_empty[st]));   // K/V stage free once every MMA issued so far retires
+        if (ptx::elect_one()) ptx::tc_commit(ptx::smem_u32(&bar_kv_empty[st]));   // K/V stage free once every MMA issued so far retires
+        __syncwarp();
         st = st_n; st_ph = ph_n;
       }
     }

@@ -165,8 +165,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   constexpr uint16_t kMask = (1u << CLUSTER) - 1;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (warp-convergent loop, one elected lane issues) =====================
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
@@ -178,6 +178,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           ptx::mbar_wait(ptx::smem_u32(&bar_empty[stage]), phase ^ 1);
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
           const uint32_t sb = sa + A_STAGE_BYTES;
+          if (ptx::elect_one()) {
           if (CLUSTER == 1) {
             const uint32_t full = ptx::smem_u32(&bar_full[stage]);
             ptx::mbar_arrive_expect_tx(full, C::STAGE_BYTES);
@@ -214,20 +215,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               ptx::tma_load_2d_2sm(sb, &tmB, full, kb * BK, n_blk * BN + cta_rank * (BN / 2));
             }
           }
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only when paired) =====================
-    if (lane == 0 && cta_rank == 0) {
+    // The whole warp runs the loop (all lanes wait on the barriers); elect.sync picks the issuing lane so that the
+    // descriptor arithmetic and the UTCHMMAs stay on the uniform datapath.
+    if (cta_rank == 0) {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM * CLUSTER, BN, A_MN, B_MN);
       // K-major  : 8-row groups 1024 B apart (SBO); LBO unused for swizzled K-major (CUTLASS sets 1)
       // MN-major : 64-element MN chunks BK*128 B apart (LBO); 8-k groups 1024 B apart (SBO)
       constexpr uint32_t a_lbo = A_MN ? BK * 128 : 16, a_sbo = 1024;
       constexpr uint32_t b_lbo = B_MN ? BK * 128 : 16, b_sbo = 1024;
-      constexpr uint32_t a_kstep = A_MN ? UMMA_K * 128 : UMMA_K * 2;  // bytes per UMMA_K advance
-      constexpr uint32_t b_kstep = B_MN ? UMMA_K * 128 : UMMA_K * 2;
+      constexpr uint32_t a_kstep = (A_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4;  // descriptor-lo units per UMMA_K advance
+      constexpr uint32_t b_kstep = (B_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4;
+      uint32_t a_lo0, a_hi, b_lo0, b_hi;
+      ptx::umma_desc_sw128_lh(smem_base, a_lbo, a_sbo, a_lo0, a_hi);
+      ptx::umma_desc_sw128_lh(smem_base + A_STAGE_BYTES, b_lbo, b_sbo, b_lo0, b_hi);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -242,23 +250,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(ptx::smem_u32(&bar_full[stage]), phase);
           ptx::tc_fence_after();
-          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
-          const uint32_t sb = sa + A_STAGE_BYTES;
+          const uint32_t a_lo = a_lo0 + stage * (C::STAGE_BYTES >> 4);
+          const uint32_t b_lo = b_lo0 + stage * (C::STAGE_BYTES >> 4);
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t ad = ptx::umma_smem_desc_sw128(sa + k * a_kstep, a_lbo, a_sbo);
-            const uint64_t bd = ptx::umma_smem_desc_sw128(sb + k * b_kstep, b_lbo, b_sbo);
-            if (CLUSTER == 1) ptx::tc_mma_f16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            else ptx::tc_mma2_f16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              if (CLUSTER == 1) ptx::tc_mma_f16_lh(d_tmem, a_lo + k * a_kstep, a_hi, b_lo + k * b_kstep, b_hi, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              else ptx::tc_mma2_f16_lh(d_tmem, a_lo + k * a_kstep, a_hi, b_lo + k * b_kstep, b_hi, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            // frees the smem slot (in both CTAs of a pair) when the MMAs retire
+            if (CLUSTER == 1) ptx::tc_commit(ptx::smem_u32(&bar_empty[stage]));
+            else ptx::tc_commit2_mc(ptx::smem_u32(&bar_empty[stage]), kMask);
+            if (kb + 1 == kb1) {   // accumulator complete (each CTA's epilogue drains its own 128 rows)
+              if (CLUSTER == 1) ptx::tc_commit(ptx::smem_u32(&bar_tmem_full[acc]));
+              else ptx::tc_commit2_mc(ptx::smem_u32(&bar_tmem_full[acc]), kMask);
+            }
           }
-          // frees the smem slot (in both CTAs of a pair) when the MMAs retire
-          if (CLUSTER == 1) ptx::tc_commit(ptx::smem_u32(&bar_empty[stage]));
-          else ptx::tc_commit2_mc(ptx::smem_u32(&bar_empty[stage]), kMask);
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        // accumulator complete (each CTA's epilogue drains its own 128 rows)
-        if (CLUSTER == 1) ptx::tc_commit(ptx::smem_u32(&bar_tmem_full[acc]));
-        else ptx::tc_commit2_mc(ptx::smem_u32(&bar_tmem_full[acc]), kMask);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }

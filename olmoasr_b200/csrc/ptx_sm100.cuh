@@ -211,6 +211,50 @@ __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// ---- lean issue path ---------------------------------------------------------------------------------------
+// The MMA-issuing warp runs its loop CONVERGENTLY (all 32 lanes wait on the mbarriers) and enters the issue region
+// through elect.sync: the compiler then keeps the whole region on the uniform datapath (UIADD3 + UTCHMMA back to
+// back).  Descriptors are passed as {lo, hi} halves: `hi` is a per-operand constant and `lo` is a precomputed base
+// plus a compile-time byte offset >> 4, so a K-step costs one uniform add per operand.  (Issuing from inside an
+// `if (lane == 0)` region cost ~12 vector->uniform instructions (R2UR ...) per descriptor and capped the attention
+// kernels at ~100+ cycles per MMA; a per-lane predicate on the instruction makes ptxas emit a serialising loop.)
+__device__ __forceinline__ void umma_desc_sw128_lh(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t& lo,
+                                                   uint32_t& hi) {
+  lo = ((saddr & 0x3FFFF) >> 4) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+  hi = ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
+}
+// one lane of a fully converged warp (the compiler keeps the region on the uniform datapath)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tc_mma_f16_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma2_f16_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
