@@ -259,13 +259,23 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
     };
 
+    // lse / delta of this thread's query row are fetched one iteration ahead (their ~1 us global-load latency used to
+    // be the top stall of the compute warps)
+    const int64_t stat_base = (static_cast<int64_t>(b) * p.H + h) * p.Tq;
+    auto load_stats = [&](int it, float& lse_o, float& dlt_o) {
+      const int qn = (i_begin + it) * BQ + r;
+      const bool ok = it < n_iter && qn < p.Tq;
+      lse_o = ok ? __ldg(p.lse + stat_base + qn) : 0.f;
+      dlt_o = ok ? __ldg(p.delta + stat_base + qn) : 0.f;
+    };
+    float lse_nx, dlt_nx;
+    load_stats(0, lse_nx, dlt_nx);
     for (int it = 0; it < n_iter; ++it) {
       const int q0 = (i_begin + it) * BQ;
       const int qi = q0 + r;
       const bool q_ok = qi < p.Tq;
-      const int64_t stat_idx = (static_cast<int64_t>(b) * p.H + h) * p.Tq + qi;
-      const float lse = q_ok ? p.lse[stat_idx] : 0.f;
-      const float dlt = q_ok ? p.delta[stat_idx] : 0.f;
+      const float lse = lse_nx, dlt = dlt_nx;
+      load_stats(it + 1, lse_nx, dlt_nx);
       int limit = kv_valid - kv0;                     // visible keys of this tile: [0, limit)
       if (p.causal) limit = min(limit, qi - kv0 + 1);
       if (!q_ok) limit = 0;
