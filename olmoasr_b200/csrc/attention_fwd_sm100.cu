@@ -240,9 +240,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int i = 0; i < BKV; ++i)
           if (i >= limit) v[i] = -INFINITY;
       }
-      float mx = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
+      // 8 independent FMNMX3 chains (a single chain of 63 dependent ops costs ~250 cycles of pure latency per tile)
+      float mxs[8];
 #pragma unroll
-      for (int i = 4; i < BKV; i += 2) mx = fmaxf(fmaxf(mx, v[i]), v[i + 1]);
+      for (int u = 0; u < 8; ++u) mxs[u] = fmaxf(v[2 * u], v[2 * u + 1]);
+#pragma unroll
+      for (int i = 16; i < BKV; i += 16)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) mxs[u] = fmaxf(fmaxf(mxs[u], v[i + 2 * u]), v[i + 2 * u + 1]);
+      const float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])), fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
       const float m_new = fmaxf(m, mx);
       const bool need = (j == 0) || ((m_new - m) * c > RESCALE_LOG2);
       const float m_next = need ? m_new : m;
@@ -268,7 +274,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       // p = 2^(s*c - m*c) (packed FFMA2), row sum (FADD2), bf16 -> swizzled smem (A operand of P V)
       const float neg = (m == -INFINITY) ? 0.f : -m * c;
       const float2 c2 = make_float2(c, c), n2 = make_float2(neg, neg);
-      float2 sum_a = make_float2(0.f, 0.f), sum_b = make_float2(0.f, 0.f);
+      float2 sums[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
       // POLY: odd pairs go through the FMA-pipe polynomial, even pairs through MUFU.EX2 (the two pipes run side by
       // side).  Masked tiles keep MUFU for every element so that -inf maps to exactly 0.
       auto emit_p = [&](auto poly_tag) {
@@ -286,7 +292,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
               float2 pe;
               if (POLY && (e & 1)) pe = exp2_poly2(x);
               else pe = make_float2(fast_exp2(x.x), fast_exp2(x.y));
-              if (e & 1) sum_b = __fadd2_rn(sum_b, pe); else sum_a = __fadd2_rn(sum_a, pe);
+              sums[e] = __fadd2_rn(sums[e], pe);
               w[e] = pack_bf16x2(pe.x, pe.y);
             }
             const int chunk = (cc & 1) * 4 + q4;       // 16-byte chunk index within the 128-byte row
@@ -303,7 +309,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_p[t]));
-      l += (sum_a.x + sum_a.y) + (sum_b.x + sum_b.y);
+      l += ((sums[0].x + sums[0].y) + (sums[1].x + sums[1].y)) + ((sums[2].x + sums[2].y) + (sums[3].x + sums[3].y));
     }
     if (n_t > 0) {
       ptx::mbar_wait(ptx::smem_u32(&bar_pv[t]), (n_t - 1) & 1);

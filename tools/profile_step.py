@@ -48,6 +48,14 @@ def main():
     for _ in range(2):
         step()
     torch.cuda.synchronize()
+    import time
+    t0 = time.perf_counter()
+    for _ in range(3):
+        step()
+    t_enq = (time.perf_counter() - t0) / 3
+    torch.cuda.synchronize()
+    t_all = (time.perf_counter() - t0) / 3
+    print(f"# host enqueue time per step {t_enq * 1e3:.1f} ms; wall per step {t_all * 1e3:.1f} ms (CPU-bound if these are close)")
     if args.no_profiler:
         step()
         torch.cuda.synchronize()
