@@ -271,8 +271,8 @@ def our_arm(args):
     prof = K.GEMM_PROFILE
     K.GEMM_PROFILE = None
     clocks = sampler.stop() if rank == 0 else None
-    gemm_flops = sum(f for f, _, _ in prof)
-    gemm_ms = sum(a.elapsed_time(b) for _, a, b in prof)
+    gemm_flops = sum(p[0] for p in prof)
+    gemm_ms = sum(p[1].elapsed_time(p[2]) for p in prof)
     ms_e2e, loss_e2e = timed(args.steps, e2e=True)
 
     if rank != 0:

@@ -45,33 +45,34 @@ struct GemmParams {
   int kblocks_total, kblocks_per_split;
   int epi;
   int raster_m;  // 1: consecutive tiles walk M first (B tile stays hot in L2) -- used when B is the larger operand
+  int tma_c;     // 1: bf16 outputs leave through the staging buffers + TMA stores (tmC / tmC2 are valid)
 };
 
 template <int BN, int CLUSTER = 1>
 struct Cfg {
   static constexpr int B_STAGE_BYTES = (BN / CLUSTER) * BK * 2;   // per CTA
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + manual 1 KB alignment slack
+  // bf16 epilogues of the 128/256-wide tiles leave through shared memory: two 32-row x 128-byte staging buffers per
+  // epilogue warp, drained by TMA bulk stores (a per-thread 16-byte store touches 32 lines per warp instruction --
+  // 4096 LSU wavefronts per tile and output, which bounded the K = 1024 GEMMs)
+  static constexpr int STG_BYTES = (BN >= 128) ? 8 * 2 * 4096 : 0;
+  static constexpr int TAIL_BYTES = 2 * BN * 4 + 256;             // bias staging + mbarriers + TMEM slot
+  static constexpr int BUDGET = 232448 - TAIL_BYTES - STG_BYTES;
+  static constexpr int STAGES = (BUDGET / STAGE_BYTES) > 8 ? 8 : (BUDGET / STAGE_BYTES);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + TAIL_BYTES;   // all dynamic, 1024-aligned base
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator buffers
 };
 
-__device__ __forceinline__ void store_bf16x32(bf16* dst, const float (&x)[32], int nvalid, bool vec) {
+__device__ __forceinline__ void store_packed_bf16x32(bf16* dst, const uint32_t (&w)[16], int nvalid, bool vec) {
   if (vec && nvalid == 32) {
     uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      uint4 u;
-      u.x = pack_bf16x2(x[8 * q + 0], x[8 * q + 1]);
-      u.y = pack_bf16x2(x[8 * q + 2], x[8 * q + 3]);
-      u.z = pack_bf16x2(x[8 * q + 4], x[8 * q + 5]);
-      u.w = pack_bf16x2(x[8 * q + 6], x[8 * q + 7]);
-      d4[q] = u;
-    }
+    for (int q = 0; q < 4; ++q) d4[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
   } else {
+    uint16_t* d = reinterpret_cast<uint16_t*>(dst);
 #pragma unroll
     for (int j = 0; j < 32; ++j)
-      if (j < nvalid) dst[j] = __float2bfloat16_rn(x[j]);
+      if (j < nvalid) d[j] = static_cast<uint16_t>(w[j >> 1] >> (16 * (j & 1)));
   }
 }
 
@@ -110,25 +111,35 @@ __device__ __forceinline__ void decode_tile(int tile, const GemmParams& p, int t
 template <int BN, int A_MN, int B_MN, int CLUSTER>
 __global__ void __launch_bounds__(384, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
                     const GemmParams p) {
   using C = Cfg<BN, CLUSTER>;
   constexpr int STAGES = C::STAGES;
 
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_full[STAGES];
-  __shared__ __align__(8) uint64_t bar_empty[STAGES];
-  __shared__ __align__(8) uint64_t bar_tmem_full[2];
-  __shared__ __align__(8) uint64_t bar_tmem_empty[2];
-  __shared__ uint32_t tmem_base_slot;
-  __shared__ __align__(16) float s_bias[2][BN];
+  // all shared memory is dynamic so that the 128B-swizzled regions start on a 1024-byte boundary without slack:
+  //   [STAGES x (A | B)] [8 warps x 2 x 4 KB output staging] [bias 2 x BN f32] [mbarriers] [TMEM slot]
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* tail = smem_raw + STAGES * C::STAGE_BYTES + C::STG_BYTES;
+  float (*s_bias)[BN] = reinterpret_cast<float (*)[BN]>(tail);
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(tail + 2 * BN * 4);
+  uint64_t* bar_empty = bar_full + STAGES;
+  uint64_t* bar_tmem_full = bar_empty + STAGES;
+  uint64_t* bar_tmem_empty = bar_tmem_full + 2;
+  uint32_t& tmem_base_slot = *reinterpret_cast<uint32_t*>(bar_tmem_empty + 2);
+  static_assert((2 * STAGES + 4) * 8 + 4 <= 256, "barrier area");
 
-  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_base = ptx::smem_u32(smem_raw);
+  if (smem_base & 1023u) __trap();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     ptx::tma_prefetch_desc(&tmA);
     ptx::tma_prefetch_desc(&tmB);
+    if (p.tma_c) {
+      ptx::tma_prefetch_desc(&tmC);
+      if (p.epi == OASR_EPI_BF16_GELU) ptx::tma_prefetch_desc(&tmC2);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -284,6 +295,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const bool vec_c = c_is_f32 ? ((p.ldc & 3) == 0) : ((p.ldc & 7) == 0);
     const bool vec_aux = (p.ldaux & 7) == 0;
     const bool use_aux = (p.epi == OASR_EPI_BF16_RESIDUAL || p.epi == OASR_EPI_BF16_GELU_BWD);
+    const bool use_tma = (BN >= 128) && p.tma_c != 0;
+    const uint32_t stg = smem_base + STAGES * C::STAGE_BYTES + (warp - 4) * 8192;   // this warp's two staging buffers
+    int sbuf = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       int n_blk, m_blk, split_unused;
       decode_tile(tile, p, tiles_mc, CLUSTER, cta_rank, m_blk, n_blk, split_unused);
@@ -314,11 +328,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll 1
       for (int ci = 0; ci < NCH; ++ci) {
         const int c = chalf * NCH + ci;
-        const int col_c = n_blk * BN + c * 32;
-        const bool aux_here = use_aux && vec_aux && row_ok && (col_c + 32 <= p.N);
+        const int col = n_blk * BN + c * 32;
+        const int nvalid = min(32, p.N - col);
+        if (use_tma && (ci & 1) == 0 && nvalid <= 0) break;   // this 64-column piece and everything right of it is outside N
+        const bool aux_here = use_aux && vec_aux && row_ok && (col + 32 <= p.N);
         uint4 auxc[4];
         if (aux_here) {   // issued before the TMEM load so both latencies overlap
-          const uint4* ap4 = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.aux) + static_cast<int64_t>(row) * p.ldaux + col_c);
+          const uint4* ap4 = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.aux) + static_cast<int64_t>(row) * p.ldaux + col);
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) auxc[q4] = ap4[q4];
         }
@@ -326,9 +342,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent `continue`
         ptx::tc_ld_32x32b_x32(t_row + c * 32, r);
         ptx::tc_wait_ld();
-        const int col = n_blk * BN + c * 32;
-        const int nvalid = min(32, p.N - col);
-        if (!row_ok || nvalid <= 0) continue;
+        if (!use_tma && (!row_ok || nvalid <= 0)) continue;
         float x[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]);
@@ -341,89 +355,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         const int64_t off = static_cast<int64_t>(row) * p.ldc + col;
-        switch (p.epi) {
-          case OASR_EPI_BF16:
-            store_bf16x32(reinterpret_cast<bf16*>(p.C) + off, x, nvalid, vec_c);
-            break;
-          case OASR_EPI_BF16_GELU: {
-            if (vec_c && nvalid == 32) {   // packed path: h = bf16(acc + b), g = bf16(gelu(h)), two elements per op
-              uint32_t hp[16], gp[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                hp[j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
-                const float2 g2 = gelu_erf2(unpack_bf16x2(hp[j]));
-                gp[j] = pack_bf16x2(g2.x, g2.y);
-              }
-              uint4* d1 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.C) + off);
-              uint4* d2 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.C2) + off);
-#pragma unroll
-              for (int q4 = 0; q4 < 4; ++q4) {
-                d1[q4] = make_uint4(hp[4 * q4], hp[4 * q4 + 1], hp[4 * q4 + 2], hp[4 * q4 + 3]);
-                d2[q4] = make_uint4(gp[4 * q4], gp[4 * q4 + 1], gp[4 * q4 + 2], gp[4 * q4 + 3]);
-              }
-            } else {
-              float g[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) { x[j] = bf16_round(x[j]); g[j] = gelu_erf(x[j]); }
-              store_bf16x32(reinterpret_cast<bf16*>(p.C) + off, x, nvalid, vec_c);
-              store_bf16x32(reinterpret_cast<bf16*>(p.C2) + off, g, nvalid, vec_c);
-            }
-            break;
-          }
-          case OASR_EPI_BF16_RESIDUAL: {
-            if (aux_here && vec_c && nvalid == 32) {   // packed: C = bf16(aux + bf16(acc + b))
-              uint4* d1 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.C) + off);
-#pragma unroll
-              for (int q4 = 0; q4 < 4; ++q4) {
-                const uint32_t aw[4] = {auxc[q4].x, auxc[q4].y, auxc[q4].z, auxc[q4].w};
-                uint32_t ow[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const int j = q4 * 8 + e * 2;
-                  const float2 y = unpack_bf16x2(pack_bf16x2(x[j], x[j + 1]));
-                  const float2 o = __fadd2_rn(unpack_bf16x2(aw[e]), y);
-                  ow[e] = pack_bf16x2(o.x, o.y);
-                }
-                d1[q4] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-              }
-            } else {
-              float a[32];
-              load_bf16x32(reinterpret_cast<const bf16*>(p.aux) + static_cast<int64_t>(row) * p.ldaux + col, a, nvalid, vec_aux);
-#pragma unroll
-              for (int j = 0; j < 32; ++j) x[j] = a[j] + bf16_round(x[j]);
-              store_bf16x32(reinterpret_cast<bf16*>(p.C) + off, x, nvalid, vec_c);
-            }
-            break;
-          }
-          case OASR_EPI_BF16_GELU_BWD: {
-            const bf16* ap = reinterpret_cast<const bf16*>(p.aux) + static_cast<int64_t>(row) * p.ldaux + col;
-            if (aux_here && vec_c && nvalid == 32) {   // packed path on the prefetched pre-activations
-              uint4* d1 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.C) + off);
-#pragma unroll
-              for (int q4 = 0; q4 < 4; ++q4) {
-                const uint32_t hw[4] = {auxc[q4].x, auxc[q4].y, auxc[q4].z, auxc[q4].w};
-                uint32_t ow[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const int j = q4 * 8 + e * 2;
-                  const float2 dg = unpack_bf16x2(pack_bf16x2(x[j], x[j + 1]));   // bf16(acc): the matmul-backward output
-                  const float2 gr = gelu_erf_grad2(unpack_bf16x2(hw[e]));
-                  const float2 o = __fmul2_rn(dg, gr);
-                  ow[e] = pack_bf16x2(o.x, o.y);
-                }
-                d1[q4] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-              }
-            } else {
-              float a[32];
-              load_bf16x32(ap, a, nvalid, vec_aux);
-#pragma unroll
-              for (int j = 0; j < 32; ++j) x[j] = bf16_round(x[j]) * gelu_erf_grad(a[j]);
-              store_bf16x32(reinterpret_cast<bf16*>(p.C) + off, x, nvalid, vec_c);
-            }
-            break;
-          }
-          case OASR_EPI_F32: {
-            float* dst = reinterpret_cast<float*>(p.C) + off;
+        if (c_is_f32) {
+          float* dst = reinterpret_cast<float*>(p.C) + off;
+          if (p.epi == OASR_EPI_F32) {
             if (vec_c && nvalid == 32) {
 #pragma unroll
               for (int j = 0; j < 8; ++j)
@@ -433,10 +367,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               for (int j = 0; j < 32; ++j)
                 if (j < nvalid) dst[j] = x[j];
             }
-            break;
-          }
-          case OASR_EPI_F32_ATOMIC_ADD: {
-            float* dst = reinterpret_cast<float*>(p.C) + off;
+          } else {
             if (vec_c && nvalid == 32) {
 #pragma unroll
               for (int j = 0; j < 8; ++j)
@@ -449,10 +380,88 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               for (int j = 0; j < 32; ++j)
                 if (j < nvalid) atomicAdd(dst + j, x[j]);
             }
+          }
+          continue;
+        }
+        // ---- bf16 epilogues: every variant ends in packed words o1 (and o2 = GELU output), two columns per word
+        uint32_t o1[16], o2[16];
+        const int nload = row_ok ? max(nvalid, 0) : 0;   // aux elements the scalar fallback may touch
+        switch (p.epi) {
+          case OASR_EPI_BF16_GELU: {   // h = bf16(acc + b), g = bf16(gelu(h))
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              o1[j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
+              const float2 g2 = gelu_erf2(unpack_bf16x2(o1[j]));
+              o2[j] = pack_bf16x2(g2.x, g2.y);
+            }
             break;
           }
-          default:
+          case OASR_EPI_BF16_RESIDUAL: {   // C = bf16(aux + bf16(acc + b))
+            if (!aux_here) {
+              float a[32];
+              load_bf16x32(reinterpret_cast<const bf16*>(p.aux) + static_cast<int64_t>(row_ok ? row : 0) * p.ldaux + col, a, nload, false);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) (&auxc[j >> 2].x)[j & 3] = pack_bf16x2(a[2 * j], a[2 * j + 1]);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float2 y = unpack_bf16x2(pack_bf16x2(x[2 * j], x[2 * j + 1]));
+              const float2 o = __fadd2_rn(unpack_bf16x2((&auxc[j >> 2].x)[j & 3]), y);
+              o1[j] = pack_bf16x2(o.x, o.y);
+            }
             break;
+          }
+          case OASR_EPI_BF16_GELU_BWD: {   // C = bf16(bf16(acc) * gelu'(aux))
+            if (!aux_here) {
+              float a[32];
+              load_bf16x32(reinterpret_cast<const bf16*>(p.aux) + static_cast<int64_t>(row_ok ? row : 0) * p.ldaux + col, a, nload, false);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) (&auxc[j >> 2].x)[j & 3] = pack_bf16x2(a[2 * j], a[2 * j + 1]);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float2 dg = unpack_bf16x2(pack_bf16x2(x[2 * j], x[2 * j + 1]));   // bf16(acc): the matmul-backward output
+              const float2 gr = gelu_erf_grad2(unpack_bf16x2((&auxc[j >> 2].x)[j & 3]));
+              const float2 o = __fmul2_rn(dg, gr);
+              o1[j] = pack_bf16x2(o.x, o.y);
+            }
+            break;
+          }
+          default: {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o1[j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
+            break;
+          }
+        }
+        if (use_tma) {
+          const bool gelu = p.epi == OASR_EPI_BF16_GELU;
+          if ((ci & 1) == 0) {   // first half of a piece: the buffer(s) about to be refilled must have been read out
+            if (lane == 0) {
+              if (gelu) ptx::tma_store_wait_read<0>(); else ptx::tma_store_wait_read<1>();
+            }
+            __syncwarp();
+          }
+          const uint32_t b1 = stg + (gelu ? 0u : static_cast<uint32_t>(sbuf) * 4096u);
+          const uint32_t rowa = lane * 128;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {   // 128B swizzle: 16-byte unit index ^ (row & 7)
+            const uint32_t sw = ((((ci & 1) * 4 + q4) ^ (lane & 7)) << 4) + rowa;
+            ptx::st_shared_v4(b1 + sw, o1[4 * q4], o1[4 * q4 + 1], o1[4 * q4 + 2], o1[4 * q4 + 3]);
+            if (gelu) ptx::st_shared_v4(stg + 4096u + sw, o2[4 * q4], o2[4 * q4 + 1], o2[4 * q4 + 2], o2[4 * q4 + 3]);
+          }
+          if ((ci & 1) == 1) {   // piece complete: hand it to the TMA engine (rows >= M and columns >= N are clipped)
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              ptx::tma_store_2d(&tmC, b1, col - 32, m_blk * BM + q * 32);
+              if (gelu) ptx::tma_store_2d(&tmC2, stg + 4096u, col - 32, m_blk * BM + q * 32);
+              ptx::tma_store_commit();
+            }
+            if (!gelu) sbuf ^= 1;
+          }
+        } else {
+          store_packed_bf16x32(reinterpret_cast<bf16*>(p.C) + off, o1, nvalid, vec_c);
+          if (p.epi == OASR_EPI_BF16_GELU) store_packed_bf16x32(reinterpret_cast<bf16*>(p.C2) + off, o2, nvalid, vec_c);
         }
       }
       ptx::tc_fence_before();
@@ -463,6 +472,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (use_tma && lane == 0) ptx::tma_store_wait<0>();   // shared memory stays valid until the engine has drained it
   }
 
   ptx::tc_fence_before();
@@ -476,7 +486,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 template <int BN, int A_MN, int B_MN, int CLUSTER>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC2,
+           const GemmParams& p, cudaStream_t st) {
   using C = Cfg<BN, CLUSTER>;
   auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, CLUSTER>;
   static bool attr_set = false;  // per instantiation
@@ -499,17 +510,17 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  OASR_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+  OASR_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmC2, p));
   return OASR_OK;
 }
 
 template <int BN, int CLUSTER>
-int dispatch_major(int a_mn, int b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                   const GemmParams& p, cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch<BN, 0, 0, CLUSTER>(tmA, tmB, p, st);
-  if (!a_mn && b_mn) return launch<BN, 0, 1, CLUSTER>(tmA, tmB, p, st);
-  if (a_mn && b_mn) return launch<BN, 1, 1, CLUSTER>(tmA, tmB, p, st);
-  return launch<BN, 1, 0, CLUSTER>(tmA, tmB, p, st);
+int dispatch_major(int a_mn, int b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                   const CUtensorMap& tmC2, const GemmParams& p, cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch<BN, 0, 0, CLUSTER>(tmA, tmB, tmC, tmC2, p, st);
+  if (!a_mn && b_mn) return launch<BN, 0, 1, CLUSTER>(tmA, tmB, tmC, tmC2, p, st);
+  if (a_mn && b_mn) return launch<BN, 1, 1, CLUSTER>(tmA, tmB, tmC, tmC2, p, st);
+  return launch<BN, 1, 0, CLUSTER>(tmA, tmB, tmC, tmC2, p, st);
 }
 
 }  // namespace
@@ -564,15 +575,31 @@ extern "C" int oasr_gemm_bf16(const void* A, int64_t lda, int a_layout, const vo
     rc = make_tmap_2d(&tmB, B, 2, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, BK, true);
   if (rc) return rc;
 
+  // bf16 outputs of the 128/256-wide tiles are written by TMA from the epilogue's staging buffers (box 64 x 32, 128B
+  // swizzle; rows >= M / columns >= N are clipped by the engine).  Needs a 16-byte aligned C with ldc % 8 == 0.
+  CUtensorMap tmC = {}, tmC2 = {};
+  static const int env_tma_c = [] { const char* e = getenv("OASR_GEMM_TMA_STORE"); return e ? atoi(e) : 1; }();
+  const bool bf16_out = epilogue <= OASR_EPI_BF16_GELU_BWD;
+  p.tma_c = (env_tma_c && bf16_out && block_n >= 128 && (ldc & 7) == 0 && (reinterpret_cast<uintptr_t>(Cout) & 15) == 0 &&
+             (epilogue != OASR_EPI_BF16_GELU || (reinterpret_cast<uintptr_t>(C2) & 15) == 0)) ? 1 : 0;
+  if (p.tma_c) {
+    rc = make_tmap_2d(&tmC, Cout, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ldc * 2, 64, 32, true);
+    if (rc) return rc;
+    if (epilogue == OASR_EPI_BF16_GELU) {
+      rc = make_tmap_2d(&tmC2, C2, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ldc * 2, 64, 32, true);
+      if (rc) return rc;
+    }
+  }
+
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // CTA pairs need >= 2 M tiles and a B tile that splits in two; OASR_GEMM_CLUSTER=1 selects the 1-CTA kernel (A/B tests)
   static const int env_cluster = [] { const char* e = getenv("OASR_GEMM_CLUSTER"); return e ? atoi(e) : 2; }();
   const bool pair = env_cluster >= 2 && p.tiles_m >= 2 && block_n >= 128;
   switch (block_n) {
-    case 256: return pair ? dispatch_major<256, 2>(a_layout, b_layout, tmA, tmB, p, st)
-                          : dispatch_major<256, 1>(a_layout, b_layout, tmA, tmB, p, st);
-    case 128: return pair ? dispatch_major<128, 2>(a_layout, b_layout, tmA, tmB, p, st)
-                          : dispatch_major<128, 1>(a_layout, b_layout, tmA, tmB, p, st);
-    default: return dispatch_major<64, 1>(a_layout, b_layout, tmA, tmB, p, st);
+    case 256: return pair ? dispatch_major<256, 2>(a_layout, b_layout, tmA, tmB, tmC, tmC2, p, st)
+                          : dispatch_major<256, 1>(a_layout, b_layout, tmA, tmB, tmC, tmC2, p, st);
+    case 128: return pair ? dispatch_major<128, 2>(a_layout, b_layout, tmA, tmB, tmC, tmC2, p, st)
+                          : dispatch_major<128, 1>(a_layout, b_layout, tmA, tmB, tmC, tmC2, p, st);
+    default: return dispatch_major<64, 1>(a_layout, b_layout, tmA, tmB, tmC, tmC2, p, st);
   }
 }

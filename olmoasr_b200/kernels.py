@@ -15,7 +15,7 @@ EPI_BF16, EPI_BF16_GELU, EPI_BF16_RESIDUAL, EPI_BF16_GELU_BWD, EPI_F32, EPI_F32_
 
 
 # When set to a list, every GEMM launch is bracketed by CUDA events on the launching stream and
-# (flops, start, end) is appended: bench.py derives the tensor-pipe roofline figure of the dominant kernel from it.
+# (flops, start, end, shape-key) is appended: bench.py derives the tensor-pipe roofline figure of the dominant kernel from it.
 GEMM_PROFILE = None
 
 
@@ -55,7 +55,7 @@ def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, out=None, out2=None, bias=Non
          M, N, K, epi, split_k, block_n, stream())
     if prof is not None:
         e1.record()
-        prof.append((2.0 * M * N * K, e0, e1))
+        prof.append((2.0 * M * N * K, e0, e1, (M, N, K, int(a_mn), int(b_mn), epi, split_k, block_n)))
     if epi == EPI_BF16_GELU:
         return out, out2
     return out

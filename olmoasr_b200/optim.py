@@ -74,8 +74,9 @@ class FusedAdamW(torch.optim.Optimizer):
         call("oasr_adamw_step", ptr(g["dev"]), ptr(g["chunks"]), g["n_chunks"], ptr(self._norm_sq), ptr(self._found_inf),
              float(inv_scale), float(self.max_grad_norm or 0.0), float(group["lr"]), b1, b2, group["eps"],
              group["weight_decay"], step, stream())
+        step_t = torch.tensor(float(step))      # one host scalar shared by every entry (torch.optim.AdamW keeps one per param)
         for p in g["params"]:
-            self.state[p]["step"] = torch.tensor(float(step))
+            self.state[p]["step"] = step_t
         return None
 
     def grad_norm(self) -> torch.Tensor:
