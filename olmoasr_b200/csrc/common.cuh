@@ -84,33 +84,34 @@ __device__ __forceinline__ float fast_ex2(float x) {
 // Two-element GELU / GELU' for GEMM epilogues: same Abramowitz-Stegun erf as erf_fast, but packed FFMA2 / FMUL2
 // arithmetic, MUFU.RCP instead of the IEEE reciprocal and one shared exp(-x^2/2) for cdf and pdf: ~10 instructions
 // per element instead of ~35 (the fc1 GELU epilogue measured 34k cycles per 128 x 256 tile against 8k of MMA).
-struct GeluPair { float2 erfv; float2 e; };   // erf(x/sqrt2) and exp(-x^2/2)
+struct GeluPair { float2 ea; float2 e; };   // erf(|x|/sqrt2) (>= 0) and exp(-x^2/2)
 __device__ __forceinline__ GeluPair gelu_core2(float2 x) {
-  const float2 z = __fmul2_rn(x, make_float2(0.70710678118654752440f, 0.70710678118654752440f));
-  const float2 az = make_float2(fabsf(z.x), fabsf(z.y));
-  const float2 d = __ffma2_rn(az, make_float2(0.3275911f, 0.3275911f), make_float2(1.0f, 1.0f));
+  // 1 / (1 + p |x| / sqrt2): |x| folds into the FFMA2 operand modifier
+  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+  const float2 d = __ffma2_rn(ax, make_float2(0.23164189f, 0.23164189f), make_float2(1.0f, 1.0f));
   const float2 t = make_float2(fast_rcp(d.x), fast_rcp(d.y));
   float2 p = __ffma2_rn(t, make_float2(1.061405429f, 1.061405429f), make_float2(-1.453152027f, -1.453152027f));
   p = __ffma2_rn(p, t, make_float2(1.421413741f, 1.421413741f));
   p = __ffma2_rn(p, t, make_float2(-0.284496736f, -0.284496736f));
   p = __ffma2_rn(p, t, make_float2(0.254829592f, 0.254829592f));
-  const float2 q = __fmul2_rn(az, az);
-  const float2 a = __fmul2_rn(q, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+  // exp(-x^2/2) = 2^(-(k x)^2), k = sqrt(log2(e) / 2)
+  const float2 y = __fmul2_rn(x, make_float2(0.84932180028801907f, 0.84932180028801907f));
+  const float2 a = __fmul2_rn(make_float2(-y.x, -y.y), y);
   GeluPair r;
   r.e = make_float2(fast_ex2(a.x), fast_ex2(a.y));
   const float2 pt = __fmul2_rn(p, t);
-  const float2 one_m = __ffma2_rn(make_float2(-pt.x, -pt.y), r.e, make_float2(1.0f, 1.0f));
-  r.erfv = make_float2(copysignf(one_m.x, z.x), copysignf(one_m.y, z.y));
+  r.ea = __ffma2_rn(make_float2(-pt.x, -pt.y), r.e, make_float2(1.0f, 1.0f));
   return r;
 }
-__device__ __forceinline__ float2 gelu_erf2(float2 x) {   // 0.5 x (1 + erf(x / sqrt 2))
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {   // 0.5 x (1 + erf(x / sqrt 2)) = hx + |hx| erf(|x| / sqrt 2)
   const GeluPair g = gelu_core2(x);
   const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
-  return __ffma2_rn(hx, g.erfv, hx);
+  return __ffma2_rn(make_float2(fabsf(hx.x), fabsf(hx.y)), g.ea, hx);
 }
 __device__ __forceinline__ float2 gelu_erf_grad2(float2 x) {   // Phi(x) + x phi(x)
   const GeluPair g = gelu_core2(x);
-  const float2 cdf = __ffma2_rn(g.erfv, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
+  const float2 se = make_float2(copysignf(g.ea.x, x.x), copysignf(g.ea.y, x.y));
+  const float2 cdf = __ffma2_rn(se, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
   const float2 xp = __fmul2_rn(x, make_float2(0.39894228040143267794f, 0.39894228040143267794f));
   return __ffma2_rn(xp, g.e, cdf);
 }
@@ -146,9 +147,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
-  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
-  return __bfloat1622float2(v);
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {   // one shift + one mask (the intrinsic costs 4-5 PRMT / IMAD)
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
 
 template <typename T>

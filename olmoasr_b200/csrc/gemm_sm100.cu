@@ -298,6 +298,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const bool use_tma = (BN >= 128) && p.tma_c != 0;
     const uint32_t stg = smem_base + STAGES * C::STAGE_BYTES + (warp - 4) * 8192;   // this warp's two staging buffers
     int sbuf = 0;
+    // residual / pre-activation tiles come in through the same staging buffers: coalesced 16-byte LDGSTS (4 rows x
+    // 128 B per warp instruction instead of 32 partial lines), then each thread reads its own row back
+    const bool aux_stage = use_tma && use_aux && vec_aux && (p.N & 7) == 0 && (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       int n_blk, m_blk, split_unused;
       decode_tile(tile, p, tiles_mc, CLUSTER, cta_rank, m_blk, n_blk, split_unused);
@@ -314,7 +317,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // aux (residual / pre-activation) rows of this thread, fetched before the accumulator is ready so that the
       // ~1 us global-load latency hides behind the MMAs (it used to be the top stall of the residual epilogue)
       constexpr int NCH = BN / 64;   // 32-column chunks per epilogue warp (1, 2 or 4)
-      if (use_aux && row_ok) {       // pull this thread's aux bytes towards L2/L1 while the accumulator is still being computed
+      auto issue_aux = [&](int piece, uint32_t buf) {   // aux columns [64 * piece, +64) of this warp's half -> buf (swizzled)
+        const int u = lane & 7, r0 = lane >> 3;
+        const int colu = n_blk * BN + (chalf * NCH + piece * 2) * 32 + u * 8;
+        const bool col_ok = colu + 8 <= p.N;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int ri = r0 + 4 * i;
+          const int grow = m_blk * BM + q * 32 + ri;
+          const bool ok = col_ok && grow < p.M;
+          const bf16* src = reinterpret_cast<const bf16*>(p.aux) + (ok ? static_cast<int64_t>(grow) * p.ldaux + colu : 0);
+          ptx::cp_async_16(buf + ri * 128 + ((u ^ (ri & 7)) << 4), src, ok ? 16u : 0u);
+        }
+        ptx::cp_async_commit();
+      };
+      if (aux_stage) {   // first piece's aux travels while the accumulator is still being computed
+        if (lane == 0) ptx::tma_store_wait_read<1>();
+        __syncwarp();
+        issue_aux(0, stg + static_cast<uint32_t>(sbuf) * 4096u);
+      } else if (use_aux && row_ok) {   // direct path: pull this thread's aux bytes towards L2
 #pragma unroll
         for (int ci = 0; ci < NCH; ++ci) {
           const int col = n_blk * BN + (chalf * NCH + ci) * 32;
@@ -331,9 +352,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int col = n_blk * BN + c * 32;
         const int nvalid = min(32, p.N - col);
         if (use_tma && (ci & 1) == 0 && nvalid <= 0) break;   // this 64-column piece and everything right of it is outside N
-        const bool aux_here = use_aux && vec_aux && row_ok && (col + 32 <= p.N);
+        const bool aux_here = aux_stage || (use_aux && vec_aux && row_ok && (col + 32 <= p.N));
         uint4 auxc[4];
-        if (aux_here) {   // issued before the TMEM load so both latencies overlap
+        if (aux_here && !aux_stage) {   // issued before the TMEM load so both latencies overlap
           const uint4* ap4 = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.aux) + static_cast<int64_t>(row) * p.ldaux + col);
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) auxc[q4] = ap4[q4];
@@ -341,6 +362,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t r[32];
         __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent `continue`
         ptx::tc_ld_32x32b_x32(t_row + c * 32, r);
+        if (aux_stage) {
+          if ((ci & 1) == 0) {   // this piece's LDGSTS have landed (all lanes' copies: wait, then warp barrier)
+            ptx::cp_async_wait_all();
+            __syncwarp();
+          }
+          const uint32_t ab = stg + static_cast<uint32_t>(sbuf) * 4096u + lane * 128;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) ptx::ld_shared_v4(ab + ((((ci & 1) * 4 + q4) ^ (lane & 7)) << 4), auxc[q4]);
+        }
         ptx::tc_wait_ld();
         if (!use_tma && (!row_ok || nvalid <= 0)) continue;
         float x[32];
@@ -351,7 +381,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 b = b4[j];
-            x[4 * j] += b.x; x[4 * j + 1] += b.y; x[4 * j + 2] += b.z; x[4 * j + 3] += b.w;
+            const float2 lo = __fadd2_rn(make_float2(x[4 * j], x[4 * j + 1]), make_float2(b.x, b.y));
+            const float2 hi = __fadd2_rn(make_float2(x[4 * j + 2], x[4 * j + 3]), make_float2(b.z, b.w));
+            x[4 * j] = lo.x; x[4 * j + 1] = lo.y; x[4 * j + 2] = hi.x; x[4 * j + 3] = hi.y;
           }
         }
         const int64_t off = static_cast<int64_t>(row) * p.ldc + col;
@@ -435,7 +467,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (use_tma) {
           const bool gelu = p.epi == OASR_EPI_BF16_GELU;
-          if ((ci & 1) == 0) {   // first half of a piece: the buffer(s) about to be refilled must have been read out
+          if ((ci & 1) == 0 && !aux_stage) {   // first half of a piece: the buffer(s) about to be refilled must have been read out
             if (lane == 0) {
               if (gelu) ptx::tma_store_wait_read<0>(); else ptx::tma_store_wait_read<1>();
             }
@@ -448,6 +480,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t sw = ((((ci & 1) * 4 + q4) ^ (lane & 7)) << 4) + rowa;
             ptx::st_shared_v4(b1 + sw, o1[4 * q4], o1[4 * q4 + 1], o1[4 * q4 + 2], o1[4 * q4 + 3]);
             if (gelu) ptx::st_shared_v4(stg + 4096u + sw, o2[4 * q4], o2[4 * q4 + 1], o2[4 * q4 + 2], o2[4 * q4 + 3]);
+          }
+          if (aux_stage && (ci & 1) == 0 && ci + 2 < NCH) {   // next piece's aux into the other buffer, under this piece's second half
+            if (lane == 0) ptx::tma_store_wait_read<0>();
+            __syncwarp();
+            issue_aux((ci >> 1) + 1, stg + static_cast<uint32_t>(sbuf ^ 1) * 4096u);
           }
           if ((ci & 1) == 1) {   // piece complete: hand it to the TMA engine (rows >= M and columns >= N are clipped)
             ptx::fence_proxy_async_smem();
