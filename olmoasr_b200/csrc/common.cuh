@@ -39,6 +39,9 @@ int num_sms();
 // swizzle128 (box_inner * elt must then be 128 bytes).
 int make_tmap_2d(CUtensorMap* out, const void* base, int elt_bytes, uint64_t inner, uint64_t outer,
                  uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, bool swizzle128);
+// swizzle_bytes: 0 (none), 64 or 128
+int make_tmap_2d_sw(CUtensorMap* out, const void* base, int elt_bytes, uint64_t inner, uint64_t outer,
+                    uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle_bytes);
 int make_tmap_3d(CUtensorMap* out, const void* base, int elt_bytes, uint64_t d0, uint64_t d1,
                  uint64_t d2, uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0,
                  uint32_t b1, uint32_t b2, bool swizzle128);

@@ -45,6 +45,7 @@ struct GemmParams {
   int kblocks_total, kblocks_per_split;
   int epi;
   int raster_m;  // 1: consecutive tiles walk M first (B tile stays hot in L2) -- used when B is the larger operand
+  int debug;
   int tma_c;     // 1: bf16 outputs leave through the staging buffers + TMA stores (tmC / tmC2 are valid)
 };
 
@@ -296,10 +297,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const bool vec_aux = (p.ldaux & 7) == 0;
     const bool use_aux = (p.epi == OASR_EPI_BF16_RESIDUAL || p.epi == OASR_EPI_BF16_GELU_BWD);
     const bool use_tma = (BN >= 128) && p.tma_c != 0;
-    const uint32_t stg = smem_base + STAGES * C::STAGE_BYTES + (warp - 4) * 8192;   // this warp's two staging buffers
-    int sbuf = 0;
-    // residual / pre-activation tiles come in through the same staging buffers: coalesced 16-byte LDGSTS (4 rows x
-    // 128 B per warp instruction instead of 32 partial lines), then each thread reads its own row back
+    // this warp's staging area: four 2 KB slots, each one 32-row x 32-column bf16 chunk (64-byte rows, 64B swizzle).
+    // A chunk is handed to the TMA engine as soon as it is staged, and a slot is refilled two (GELU: o1 in slots 0/1,
+    // o2 in slots 2/3) or four chunks later, so the drain latency of the bulk store is never waited for.
+    const uint32_t stg = smem_base + STAGES * C::STAGE_BYTES + (warp - 4) * 8192;
+    uint32_t slotc = 0;   // chunks staged so far by this warp
+    // residual / pre-activation chunks come in through the same slots: coalesced 16-byte LDGSTS (8 rows x 64 B per
+    // warp instruction instead of 32 partial lines), then each thread reads its own row back
     const bool aux_stage = use_tma && use_aux && vec_aux && (p.N & 7) == 0 && (reinterpret_cast<uintptr_t>(p.aux) & 15) == 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       int n_blk, m_blk, split_unused;
@@ -317,24 +321,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // aux (residual / pre-activation) rows of this thread, fetched before the accumulator is ready so that the
       // ~1 us global-load latency hides behind the MMAs (it used to be the top stall of the residual epilogue)
       constexpr int NCH = BN / 64;   // 32-column chunks per epilogue warp (1, 2 or 4)
-      auto issue_aux = [&](int piece, uint32_t buf) {   // aux columns [64 * piece, +64) of this warp's half -> buf (swizzled)
-        const int u = lane & 7, r0 = lane >> 3;
-        const int colu = n_blk * BN + (chalf * NCH + piece * 2) * 32 + u * 8;
+      auto issue_aux = [&](int ci, uint32_t buf) {   // aux columns of chunk ci of this warp -> slot `buf` (swizzled)
+        const int u = lane & 3, r0 = lane >> 2;
+        const int colu = n_blk * BN + (chalf * NCH + ci) * 32 + u * 8;
         const bool col_ok = colu + 8 <= p.N;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int ri = r0 + 4 * i;
+        for (int i = 0; i < 4; ++i) {
+          const int ri = r0 + 8 * i;
           const int grow = m_blk * BM + q * 32 + ri;
           const bool ok = col_ok && grow < p.M;
           const bf16* src = reinterpret_cast<const bf16*>(p.aux) + (ok ? static_cast<int64_t>(grow) * p.ldaux + colu : 0);
-          ptx::cp_async_16(buf + ri * 128 + ((u ^ (ri & 7)) << 4), src, ok ? 16u : 0u);
+          ptx::cp_async_16(buf + ri * 64 + ((u ^ ((ri >> 1) & 3)) << 4), src, ok ? 16u : 0u);
         }
         ptx::cp_async_commit();
       };
-      if (aux_stage) {   // first piece's aux travels while the accumulator is still being computed
-        if (lane == 0) ptx::tma_store_wait_read<1>();
+      if (aux_stage) {   // first chunk's aux travels while the accumulator is still being computed
+        if (lane == 0) ptx::tma_store_wait_read<3>();
         __syncwarp();
-        issue_aux(0, stg + static_cast<uint32_t>(sbuf) * 4096u);
+        issue_aux(0, stg + (slotc & 3u) * 2048u);
       } else if (use_aux && row_ok) {   // direct path: pull this thread's aux bytes towards L2
 #pragma unroll
         for (int ci = 0; ci < NCH; ++ci) {
@@ -351,7 +355,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int c = chalf * NCH + ci;
         const int col = n_blk * BN + c * 32;
         const int nvalid = min(32, p.N - col);
-        if (use_tma && (ci & 1) == 0 && nvalid <= 0) break;   // this 64-column piece and everything right of it is outside N
+        if (use_tma && nvalid <= 0) break;   // this chunk and everything right of it is outside N
         const bool aux_here = aux_stage || (use_aux && vec_aux && row_ok && (col + 32 <= p.N));
         uint4 auxc[4];
         if (aux_here && !aux_stage) {   // issued before the TMEM load so both latencies overlap
@@ -363,13 +367,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent `continue`
         ptx::tc_ld_32x32b_x32(t_row + c * 32, r);
         if (aux_stage) {
-          if ((ci & 1) == 0) {   // this piece's LDGSTS have landed (all lanes' copies: wait, then warp barrier)
-            ptx::cp_async_wait_all();
-            __syncwarp();
-          }
-          const uint32_t ab = stg + static_cast<uint32_t>(sbuf) * 4096u + lane * 128;
+          ptx::cp_async_wait_all();   // this chunk's LDGSTS have landed (all lanes' copies: wait, then warp barrier)
+          __syncwarp();
+          const uint32_t ab = stg + (slotc & 3u) * 2048u + lane * 64;
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) ptx::ld_shared_v4(ab + ((((ci & 1) * 4 + q4) ^ (lane & 7)) << 4), auxc[q4]);
+          for (int q4 = 0; q4 < 4; ++q4) ptx::ld_shared_v4(ab + ((q4 ^ ((lane >> 1) & 3)) << 4), auxc[q4]);
+          if (ci + 1 < NCH && col + 32 < p.N) {   // next chunk's aux into the next slot (its last store was 3 groups ago)
+            if (lane == 0) ptx::tma_store_wait_read<2>();
+            __syncwarp();
+            issue_aux(ci + 1, stg + ((slotc + 1) & 3u) * 2048u);
+          }
         }
         ptx::tc_wait_ld();
         if (!use_tma && (!row_ok || nvalid <= 0)) continue;
@@ -423,6 +430,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               o1[j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
+              if (p.debug & 1) { o2[j] = o1[j]; continue; }
               const float2 g2 = gelu_erf2(unpack_bf16x2(o1[j]));
               o2[j] = pack_bf16x2(g2.x, g2.y);
             }
@@ -467,35 +475,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (use_tma) {
           const bool gelu = p.epi == OASR_EPI_BF16_GELU;
-          if ((ci & 1) == 0 && !aux_stage) {   // first half of a piece: the buffer(s) about to be refilled must have been read out
+          if (!aux_stage) {   // the slot(s) about to be refilled must have been read out by the engine
             if (lane == 0) {
-              if (gelu) ptx::tma_store_wait_read<0>(); else ptx::tma_store_wait_read<1>();
+              if (gelu) ptx::tma_store_wait_read<1>(); else ptx::tma_store_wait_read<3>();
             }
             __syncwarp();
           }
-          const uint32_t b1 = stg + (gelu ? 0u : static_cast<uint32_t>(sbuf) * 4096u);
-          const uint32_t rowa = lane * 128;
+          const uint32_t b1 = stg + (gelu ? (slotc & 1u) : (slotc & 3u)) * 2048u;
+          const uint32_t b2 = b1 + 4096u;
+          const uint32_t rowa = lane * 64;
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {   // 128B swizzle: 16-byte unit index ^ (row & 7)
-            const uint32_t sw = ((((ci & 1) * 4 + q4) ^ (lane & 7)) << 4) + rowa;
+          for (int q4 = 0; q4 < 4; ++q4) {   // 64B swizzle: 16-byte unit index ^ ((row >> 1) & 3)
+            const uint32_t sw = ((q4 ^ ((lane >> 1) & 3)) << 4) + rowa;
             ptx::st_shared_v4(b1 + sw, o1[4 * q4], o1[4 * q4 + 1], o1[4 * q4 + 2], o1[4 * q4 + 3]);
-            if (gelu) ptx::st_shared_v4(stg + 4096u + sw, o2[4 * q4], o2[4 * q4 + 1], o2[4 * q4 + 2], o2[4 * q4 + 3]);
+            if (gelu) ptx::st_shared_v4(b2 + sw, o2[4 * q4], o2[4 * q4 + 1], o2[4 * q4 + 2], o2[4 * q4 + 3]);
           }
-          if (aux_stage && (ci & 1) == 0 && ci + 2 < NCH) {   // next piece's aux into the other buffer, under this piece's second half
-            if (lane == 0) ptx::tma_store_wait_read<0>();
-            __syncwarp();
-            issue_aux((ci >> 1) + 1, stg + static_cast<uint32_t>(sbuf ^ 1) * 4096u);
+          ptx::fence_proxy_async_smem();   // chunk complete: hand it to the TMA engine (rows >= M / columns >= N are clipped)
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_2d(&tmC, b1, col, m_blk * BM + q * 32);
+            if (gelu) ptx::tma_store_2d(&tmC2, b2, col, m_blk * BM + q * 32);
+            ptx::tma_store_commit();
           }
-          if ((ci & 1) == 1) {   // piece complete: hand it to the TMA engine (rows >= M and columns >= N are clipped)
-            ptx::fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              ptx::tma_store_2d(&tmC, b1, col - 32, m_blk * BM + q * 32);
-              if (gelu) ptx::tma_store_2d(&tmC2, stg + 4096u, col - 32, m_blk * BM + q * 32);
-              ptx::tma_store_commit();
-            }
-            if (!gelu) sbuf ^= 1;
-          }
+          ++slotc;
         } else {
           store_packed_bf16x32(reinterpret_cast<bf16*>(p.C) + off, o1, nvalid, vec_c);
           if (p.epi == OASR_EPI_BF16_GELU) store_packed_bf16x32(reinterpret_cast<bf16*>(p.C2) + off, o2, nvalid, vec_c);
@@ -612,18 +614,20 @@ extern "C" int oasr_gemm_bf16(const void* A, int64_t lda, int a_layout, const vo
     rc = make_tmap_2d(&tmB, B, 2, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, BK, true);
   if (rc) return rc;
 
-  // bf16 outputs of the 128/256-wide tiles are written by TMA from the epilogue's staging buffers (box 64 x 32, 128B
+  // bf16 outputs of the 128/256-wide tiles are written by TMA from the epilogue's staging buffers (box 32 x 32, 64B
   // swizzle; rows >= M / columns >= N are clipped by the engine).  Needs a 16-byte aligned C with ldc % 8 == 0.
+  static const int env_dbg = [] { const char* e = getenv("OASR_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
+  p.debug = env_dbg;
   CUtensorMap tmC = {}, tmC2 = {};
   static const int env_tma_c = [] { const char* e = getenv("OASR_GEMM_TMA_STORE"); return e ? atoi(e) : 1; }();
   const bool bf16_out = epilogue <= OASR_EPI_BF16_GELU_BWD;
   p.tma_c = (env_tma_c && bf16_out && block_n >= 128 && (ldc & 7) == 0 && (reinterpret_cast<uintptr_t>(Cout) & 15) == 0 &&
              (epilogue != OASR_EPI_BF16_GELU || (reinterpret_cast<uintptr_t>(C2) & 15) == 0)) ? 1 : 0;
   if (p.tma_c) {
-    rc = make_tmap_2d(&tmC, Cout, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ldc * 2, 64, 32, true);
+    rc = make_tmap_2d_sw(&tmC, Cout, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ldc * 2, 32, 32, 64);
     if (rc) return rc;
     if (epilogue == OASR_EPI_BF16_GELU) {
-      rc = make_tmap_2d(&tmC2, C2, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ldc * 2, 64, 32, true);
+      rc = make_tmap_2d_sw(&tmC2, C2, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ldc * 2, 32, 32, 64);
       if (rc) return rc;
     }
   }
