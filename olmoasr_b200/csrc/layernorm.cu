@@ -67,112 +67,136 @@ layernorm_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w, co
   }
 }
 
-// Backward.  One warp per row computes dx; the parameter gradients (column sums of dy*xhat and dy) go through a
-// shared-memory staging tile: each group of 8 rows (one per warp) is written to smem, then thread t folds the 8 rows of
-// its own columns into two or three private accumulators.  This keeps the kernel at ~100 registers (the previous
-// all-in-registers version needed 214 and ran at one 8-warp block per SM, 23 % of the HBM roofline).
+// Backward.  One warp per row (grid-stride), lane l owns the same 8-column vectors l, l+32, ... of every row it visits,
+// so the parameter gradients (column sums of dy*xhat and dy) accumulate in that lane's registers with no shared-memory
+// traffic and no block barrier inside the row loop; the 8 warps of a block are folded through shared memory once at
+// the end, then one atomicAdd per column and block.  x and dy stay packed (bf16) in registers between the statistics
+// pass and the dx pass and are unpacked twice -- 32 registers instead of 64.  (History: all-fp32-in-registers needed
+// 214 registers -> 23 % of the HBM roofline; staging every row through shared memory with two __syncthreads per 8
+// rows -> 37 %.)
 template <int NV>
 __global__ void __launch_bounds__(256, 2)
 layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ w,
                      const float* __restrict__ mean, const float* __restrict__ rstd,
                      const bf16* __restrict__ dres, bf16* __restrict__ dx, float* __restrict__ dw,
                      float* __restrict__ db, int64_t rows, int d) {
-  extern __shared__ __align__(16) float stage[];  // [2][8][d]: dy*xhat, dy
-  float* s_a = stage;
-  float* s_b = stage + 8 * d;
+  extern __shared__ __align__(16) float fold[];  // [8][d], used once at the end
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nvec = d >> 3;
-  constexpr int MAXC = (NV * 256 + 255) / 256;  // columns per thread in the fold (d <= NV * 256)
-  float acc_w[MAXC], acc_b[MAXC];
+  float2 acc_w[NV][4], acc_b[NV][4];
 #pragma unroll
-  for (int i = 0; i < MAXC; ++i) { acc_w[i] = 0.f; acc_b[i] = 0.f; }
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc_w[i][j] = make_float2(0.f, 0.f); acc_b[i][j] = make_float2(0.f, 0.f); }
 
-  const int64_t n_groups = (rows + 7) / 8;
-  for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-    const int64_t row = grp * 8 + warp;
-    const bool row_ok = row < rows;
-    float xh[NV][8], g[NV][8];
-    float s1 = 0.f, s2 = 0.f, rs = 0.f;
-    if (row_ok) {
-      const uint4* xr = reinterpret_cast<const uint4*>(x + row * d);
-      const uint4* gr = reinterpret_cast<const uint4*>(dy + row * d);
-      const float mu = mean[row];
-      rs = rstd[row];
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp; row < rows; row += static_cast<int64_t>(gridDim.x) * 8) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + row * d);
+    const uint4* gr = reinterpret_cast<const uint4*>(dy + row * d);
+    const uint4* rr = dres ? reinterpret_cast<const uint4*>(dres + row * d) : nullptr;
+    uint4 ux[NV], ug[NV];
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int vi = lane + 32 * i;
-        if (vi < nvec) {
-          const uint4 ux = xr[vi], ug = gr[vi];
-          const float4 w0 = __ldg(reinterpret_cast<const float4*>(w) + 2 * vi), w1 = __ldg(reinterpret_cast<const float4*>(w) + 2 * vi + 1);
-          const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-          float2 a0 = unpack_bf16x2(ux.x), a1 = unpack_bf16x2(ux.y), a2 = unpack_bf16x2(ux.z), a3 = unpack_bf16x2(ux.w);
-          float2 c0 = unpack_bf16x2(ug.x), c1 = unpack_bf16x2(ug.y), c2 = unpack_bf16x2(ug.z), c3 = unpack_bf16x2(ug.w);
-          const float xv[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
-          const float gv[8] = {c0.x, c0.y, c1.x, c1.y, c2.x, c2.y, c3.x, c3.y};
-          float pa[8];
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < nvec) { ux[i] = xr[vi]; ug[i] = gr[vi]; }
+      else { ux[i] = make_uint4(0, 0, 0, 0); ug[i] = make_uint4(0, 0, 0, 0); }
+    }
+    {   // pull the next row this warp will visit (and this row's residual gradient) into L2 while this one is processed:
+        // one prefetch per 128-byte line (lanes 0, 8, 16, 24 of every 32-vector group)
+      const int64_t nrow = row + static_cast<int64_t>(gridDim.x) * 8;
+      if ((lane & 7) == 0) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            xh[i][j] = (xv[j] - mu) * rs;
-            pa[j] = gv[j] * xh[i][j];
-            g[i][j] = gv[j] * ww[j];
-            s1 += g[i][j];
-            s2 += g[i][j] * xh[i][j];
+        for (int i = 0; i < NV; ++i) {
+          const int vi = lane + 32 * i;
+          if (vi < nvec) {
+            if (rr) asm volatile("prefetch.global.L2 [%0];" ::"l"(rr + vi));
+            if (nrow < rows) {
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint4*>(x + nrow * d) + vi));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint4*>(dy + nrow * d) + vi));
+            }
           }
-          float4* da = reinterpret_cast<float4*>(s_a + warp * d + vi * 8);
-          float4* dbp = reinterpret_cast<float4*>(s_b + warp * d + vi * 8);
-          da[0] = make_float4(pa[0], pa[1], pa[2], pa[3]);
-          da[1] = make_float4(pa[4], pa[5], pa[6], pa[7]);
-          dbp[0] = make_float4(gv[0], gv[1], gv[2], gv[3]);
-          dbp[1] = make_float4(gv[4], gv[5], gv[6], gv[7]);
         }
       }
-    } else {
-      for (int c = lane; c < d; c += 32) { s_a[warp * d + c] = 0.f; s_b[warp * d + c] = 0.f; }
     }
-    s1 = warp_sum(s1) / d;
-    s2 = warp_sum(s2) / d;
-    if (row_ok) {
-      uint4* dxr = reinterpret_cast<uint4*>(dx + row * d);
-      const uint4* rr = dres ? reinterpret_cast<const uint4*>(dres + row * d) : nullptr;
+    const float mu = mean[row], rs = rstd[row];
+    const float2 mu2 = make_float2(mu, mu), rs2 = make_float2(rs, rs);
+    float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int vi = lane + 32 * i;
-        if (vi < nvec) {
-          float o[8];
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < nvec) {
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(w) + 2 * vi), w1 = __ldg(reinterpret_cast<const float4*>(w) + 2 * vi + 1);
+        const float2 ww[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y), make_float2(w1.z, w1.w)};
+        const uint32_t xw[4] = {ux[i].x, ux[i].y, ux[i].z, ux[i].w};
+        const uint32_t gw[4] = {ug[i].x, ug[i].y, ug[i].z, ug[i].w};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = rs * (g[i][j] - s1 - xh[i][j] * s2);
+        for (int j = 0; j < 4; ++j) {
+          const float2 xh = __fmul2_rn(__fadd2_rn(unpack_bf16x2(xw[j]), make_float2(-mu, -mu)), rs2);
+          const float2 g = unpack_bf16x2(gw[j]);
+          const float2 gwj = __fmul2_rn(g, ww[j]);
+          s1 = __fadd2_rn(s1, gwj);
+          s2 = __ffma2_rn(gwj, xh, s2);
+          acc_w[i][j] = __ffma2_rn(g, xh, acc_w[i][j]);
+          acc_b[i][j] = __fadd2_rn(acc_b[i][j], g);
+        }
+      }
+    }
+    (void)mu2;
+    const float m1 = warp_sum(s1.x + s1.y) / d;
+    const float m2 = warp_sum(s2.x + s2.y) / d;
+    uint4* dxr = reinterpret_cast<uint4*>(dx + row * d);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < nvec) {
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(w) + 2 * vi), w1 = __ldg(reinterpret_cast<const float4*>(w) + 2 * vi + 1);
+        const float2 ww[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y), make_float2(w1.z, w1.w)};
+        const uint32_t xw[4] = {ux[i].x, ux[i].y, ux[i].z, ux[i].w};
+        const uint32_t gw[4] = {ug[i].x, ug[i].y, ug[i].z, ug[i].w};
+        uint4 ur = make_uint4(0, 0, 0, 0);
+        if (rr) ur = rr[vi];
+        const uint32_t rw[4] = {ur.x, ur.y, ur.z, ur.w};
+        uint32_t ow[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 xh = __fmul2_rn(__fadd2_rn(unpack_bf16x2(xw[j]), make_float2(-mu, -mu)), rs2);
+          const float2 gwj = __fmul2_rn(unpack_bf16x2(gw[j]), ww[j]);
+          // rs * (g*w - mean(g*w) - xhat * mean(g*w*xhat))
+          float2 o = __ffma2_rn(xh, make_float2(-m2, -m2), __fadd2_rn(gwj, make_float2(-m1, -m1)));
+          o = __fmul2_rn(o, rs2);
           if (rr) {
-            const uint4 ur = rr[vi];
-            float2 r0 = unpack_bf16x2(ur.x), r1 = unpack_bf16x2(ur.y), r2 = unpack_bf16x2(ur.z), r3 = unpack_bf16x2(ur.w);
-            const float rv[8] = {r0.x, r0.y, r1.x, r1.y, r2.x, r2.y, r3.x, r3.y};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = rv[j] + bf16_round(o[j]);
+            const float2 ob = unpack_bf16x2(pack_bf16x2(o.x, o.y));   // bf16(dx_ln) first, like autograd's accumulation
+            o = __fadd2_rn(unpack_bf16x2(rw[j]), ob);
           }
-          uint4 u;
-          u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
-          u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
-          dxr[vi] = u;
+          ow[j] = pack_bf16x2(o.x, o.y);
         }
+        dxr[vi] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
       }
     }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < MAXC; ++i) {
-      const int c = threadIdx.x + i * 256;
-      if (c < d) {
-        float a = 0.f, b = 0.f;
-#pragma unroll
-        for (int r = 0; r < 8; ++r) { a += s_a[r * d + c]; b += s_b[r * d + c]; }
-        acc_w[i] += a; acc_b[i] += b;
-      }
-    }
-    __syncthreads();
   }
+
+  // fold the 8 warps' accumulators (two passes through one [8][d] buffer), one global atomic per column and block
 #pragma unroll
-  for (int i = 0; i < MAXC; ++i) {
-    const int c = threadIdx.x + i * 256;
-    if (c < d) { atomicAdd(dw + c, acc_w[i]); atomicAdd(db + c, acc_b[i]); }
+  for (int pass = 0; pass < 2; ++pass) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < nvec) {
+        float4* dst = reinterpret_cast<float4*>(fold + warp * d + vi * 8);
+        const float2* a = pass == 0 ? acc_w[i] : acc_b[i];
+        dst[0] = make_float4(a[0].x, a[0].y, a[1].x, a[1].y);
+        dst[1] = make_float4(a[2].x, a[2].y, a[3].x, a[3].y);
+      }
+    }
+    __syncthreads();
+    float* out = pass == 0 ? dw : db;
+    for (int c = threadIdx.x; c < d; c += 256) {
+      float t = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) t += fold[r * d + c];
+      atomicAdd(out + c, t);
+    }
   }
 }
 
@@ -219,12 +243,12 @@ extern "C" int oasr_layernorm_bwd(const void* dy, const void* x, const float* we
   int64_t blocks = ceil_div(rows, wpb);
   const int64_t cap = static_cast<int64_t>(num_sms()) * 2;  // 2 resident blocks per SM; few blocks => few global atomics
   if (blocks > cap) blocks = cap;
-  const size_t smem = 2 * 8 * d * sizeof(float);
+  const size_t smem = 8 * d * sizeof(float);
 #define OASR_LN_BWD(NVv)                                                                                              \
   do {                                                                                                                 \
     static bool attr_set = false;                                                                                      \
     if (!attr_set) {                                                                                                   \
-      OASR_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_kernel<NVv>, cudaFuncAttributeMaxDynamicSharedMemorySize, NVv * 256 * 64)); \
+      OASR_CUDA_OK(cudaFuncSetAttribute(layernorm_bwd_kernel<NVv>, cudaFuncAttributeMaxDynamicSharedMemorySize, NVv * 256 * 32)); \
       attr_set = true;                                                                                                 \
     }                                                                                                                  \
     layernorm_bwd_kernel<NVv><<<(int)blocks, wpb * 32, smem, st>>>(                                                    \
