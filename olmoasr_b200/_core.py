@@ -14,6 +14,7 @@ MN-major UMMA descriptors, so nothing is transposed in HBM.
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Iterable, Optional
 
 import numpy as np
@@ -114,6 +115,46 @@ def bias_grad(dy: Tensor, n: Optional[int] = None, pool: Optional[_ZeroPool] = N
     n = dy.shape[1] if n is None else n
     db = pool.take(n) if pool is not None else torch.zeros(n, device=dy.device, dtype=torch.float32)
     return K.colsum_(dy, db, n)
+
+
+# ----------------------------------------------------------------------------------------------------
+# Weight / bias gradients of a block are leaves of the backward graph: nothing downstream in the same backward reads
+# them.  They are enqueued on a second CUDA stream so that their CTAs fill the tail waves (and launch gaps) of the
+# dgrad / attention / LayerNorm chain on the main stream -- e.g. the decoder's 14336 x 1024 x 1024 GEMMs are 3.03
+# waves of 256 x 256 tiles on 74 SM pairs, i.e. a quarter of their time runs on 2 pairs.  Every block joins the side
+# stream before its backward returns, so gradients are complete in main-stream order (DDP hooks, optimizer).
+SIDE_STREAM = os.environ.get("OASR_SIDE_STREAM", "1") != "0"
+_side_streams: Dict[int, "torch.cuda.Stream"] = {}
+
+
+class _Side:
+    def __init__(self, device):
+        self.on = SIDE_STREAM and device.type == "cuda"
+        if self.on:
+            idx = device.index if device.index is not None else torch.cuda.current_device()
+            if idx not in _side_streams:
+                _side_streams[idx] = torch.cuda.Stream(device=idx)
+            self.side = _side_streams[idx]
+            self.main = torch.cuda.current_stream(idx)
+
+    def run(self, fn, *keep):
+        """fn() on the side stream, after everything enqueued on the main stream so far.  `keep`: main-stream tensors
+        fn reads that may be released before join() (none today: locals live until backward returns)."""
+        if not self.on:
+            return fn()
+        self.side.wait_stream(self.main)
+        with torch.cuda.stream(self.side):
+            out = fn()
+        for t in keep:
+            t.record_stream(self.side)
+        for t in (out if isinstance(out, (tuple, list)) else (out,)):
+            if isinstance(t, Tensor):
+                t.record_stream(self.main)   # allocated from the side stream's pool, consumed on the main stream
+        return out
+
+    def join(self):
+        if self.on:
+            self.main.wait_stream(self.side)
 
 
 def kv_len_from_padding_mask(padding_mask: Tensor) -> Tensor:
@@ -316,11 +357,14 @@ class _BlockFn(torch.autograd.Function):
         z = pool.take
 
         # ---- MLP: x3 = x2 + fc2(gelu(fc1(ln(x2))))
-        grads["mlp.2.weight"] = linear_wgrad(dx3, g)
-        grads["mlp.2.bias"] = bias_grad(dx3, pool=pool)
+        side = _Side(dev)
+        if side.on:
+            pool.buf.record_stream(side.side)
+        grads["mlp.2.weight"] = side.run(lambda: linear_wgrad(dx3, g))
+        grads["mlp.2.bias"] = side.run(lambda: bias_grad(dx3, pool=pool))
         dh = linear_dgrad(dx3, sh["w2"], epi=K.EPI_BF16_GELU_BWD, aux=h)
-        grads["mlp.0.weight"] = linear_wgrad(dh, ln2)
-        grads["mlp.0.bias"] = bias_grad(dh, pool=pool)
+        grads["mlp.0.weight"] = side.run(lambda: linear_wgrad(dh, ln2))
+        grads["mlp.0.bias"] = side.run(lambda: bias_grad(dh, pool=pool))
         dln2 = linear_dgrad(dh, sh["w1"])
         grads["mlp_ln.weight"], grads["mlp_ln.bias"] = z(d), z(d)
         dx2 = K.layernorm_bwd(dln2, x2, blk.mlp_ln.weight, mean2, rstd2, grads["mlp_ln.weight"], grads["mlp_ln.bias"],
@@ -328,17 +372,17 @@ class _BlockFn(torch.autograd.Function):
         dxa = None
         if cross:
             # ---- cross attention: x2 = x1 + out(attn(q(ln(x1)), kv(xa)))
-            grads["cross_attn.out.weight"] = linear_wgrad(dx2, co)
-            grads["cross_attn.out.bias"] = bias_grad(dx2, pool=pool)
+            grads["cross_attn.out.weight"] = side.run(lambda: linear_wgrad(dx2, co))
+            grads["cross_attn.out.bias"] = side.run(lambda: bias_grad(dx2, pool=pool))
             dco = linear_dgrad(dx2, sh["wco"])
             dqc = torch.empty_like(qc)
             dkvc = torch.empty_like(kvc)
             K.attention_bwd(qc, kvc[:, :d], kvc[:, d:], co, dco, lsec, B, H, T, Ta, dq=dqc, dk=dkvc[:, :d], dv=dkvc[:, d:])
-            grads["cross_attn.query.weight"] = linear_wgrad(dqc, lnc)
-            grads["cross_attn.query.bias"] = bias_grad(dqc, pool=pool)
-            dwkv = linear_wgrad(dkvc, xa)
+            grads["cross_attn.query.weight"] = side.run(lambda: linear_wgrad(dqc, lnc))
+            grads["cross_attn.query.bias"] = side.run(lambda: bias_grad(dqc, pool=pool))
+            dwkv = side.run(lambda: linear_wgrad(dkvc, xa))
             grads["cross_attn.key.weight"], grads["cross_attn.value.weight"] = dwkv[:d], dwkv[d:]
-            grads["cross_attn.value.bias"] = bias_grad(dkvc, pool=pool)[d:]
+            grads["cross_attn.value.bias"] = side.run(lambda: bias_grad(dkvc, pool=pool))[d:]
             dxa = linear_dgrad(dkvc, sh["wckv"])
             dlnc = linear_dgrad(dqc, sh["wcq"])
             grads["cross_attn_ln.weight"], grads["cross_attn_ln.bias"] = z(d), z(d)
@@ -347,20 +391,21 @@ class _BlockFn(torch.autograd.Function):
         else:
             dx1 = dx2
         # ---- self attention: x1 = x + out(attn(qkv(ln(x))))
-        grads["attn.out.weight"] = linear_wgrad(dx1, ao)
-        grads["attn.out.bias"] = bias_grad(dx1, pool=pool)
+        grads["attn.out.weight"] = side.run(lambda: linear_wgrad(dx1, ao))
+        grads["attn.out.bias"] = side.run(lambda: bias_grad(dx1, pool=pool))
         dao = linear_dgrad(dx1, sh["wo"])
         dqkv = torch.empty_like(qkv)
         K.attention_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], ao, dao, lse, B, H, T, T, causal=causal, kv_len=kv_len,
                         dq=dqkv[:, :d], dk=dqkv[:, d:2 * d], dv=dqkv[:, 2 * d:])
-        dw = linear_wgrad(dqkv, ln1)
+        dw = side.run(lambda: linear_wgrad(dqkv, ln1))
         grads["attn.query.weight"], grads["attn.key.weight"], grads["attn.value.weight"] = dw[:d], dw[d:2 * d], dw[2 * d:]
-        db = bias_grad(dqkv, pool=pool)
+        db = side.run(lambda: bias_grad(dqkv, pool=pool))
         grads["attn.query.bias"], grads["attn.value.bias"] = db[:d], db[2 * d:]
         dln1 = linear_dgrad(dqkv, sh["wqkv"])
         grads["attn_ln.weight"], grads["attn_ln.bias"] = z(d), z(d)
         dx = K.layernorm_bwd(dln1, x, blk.attn_ln.weight, mean1, rstd1, grads["attn_ln.weight"], grads["attn_ln.bias"],
                              dresidual=dx1)
+        side.join()
         return (None, None, None, None, None, None, dx, dxa, *[grads[n] for n in blk._param_names])
 
 

@@ -49,7 +49,6 @@ struct BwdParams {
   int64_t lddk, lddv;
   int B, H, Tq, Tkv;
   int causal;
-  int debug;   // profiling experiments only (OASR_DEBUG_ATTN_BWD): bit 0 = skip the dQ reduce-add (wrong results)
   float scale, scale_log2;
 };
 
@@ -252,7 +251,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
       ptx::fence_proxy_async_smem();
       asm volatile("bar.sync %0, 128;" ::"r"(1 + chalf) : "memory");
-      if (issuer && !(p.debug & 1)) {
+      if (issuer) {
         // rows past Tq carry exact zeros (their P and dS rows are zero), rows past the tensor are clipped by TMA
         ptx::tma_reduce_add_2d(&tmDQ, sDQh, h * HD + chalf * 32, b * p.Tq + (i_begin + it) * BQ);
         ptx::tma_store_commit();
@@ -466,8 +465,6 @@ extern "C" int oasr_attention_bwd(const void* q, int64_t ldq, const void* k, int
   p.lse = lse; p.delta = delta; p.dq_accum = dq_accum; p.dk = (bf16*)dk; p.dv = (bf16*)dv; p.kv_len = kv_len;
   p.lddk = lddk; p.lddv = lddv; p.B = (int)B; p.H = (int)H; p.Tq = (int)Tq; p.Tkv = (int)Tkv; p.causal = causal;
   p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
-  static const int debug_flags = [] { const char* e = getenv("OASR_DEBUG_ATTN_BWD"); return e ? atoi(e) : 0; }();
-  p.debug = debug_flags;
   static bool attr_set = false;
   if (!attr_set) {
     OASR_CUDA_OK(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));

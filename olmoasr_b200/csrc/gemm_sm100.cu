@@ -45,7 +45,6 @@ struct GemmParams {
   int kblocks_total, kblocks_per_split;
   int epi;
   int raster_m;  // 1: consecutive tiles walk M first (B tile stays hot in L2) -- used when B is the larger operand
-  int debug;
   int tma_c;     // 1: bf16 outputs leave through the staging buffers + TMA stores (tmC / tmC2 are valid)
 };
 
@@ -430,7 +429,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               o1[j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
-              if (p.debug & 1) { o2[j] = o1[j]; continue; }
               const float2 g2 = gelu_erf2(unpack_bf16x2(o1[j]));
               o2[j] = pack_bf16x2(g2.x, g2.y);
             }
@@ -616,8 +614,6 @@ extern "C" int oasr_gemm_bf16(const void* A, int64_t lda, int a_layout, const vo
 
   // bf16 outputs of the 128/256-wide tiles are written by TMA from the epilogue's staging buffers (box 32 x 32, 64B
   // swizzle; rows >= M / columns >= N are clipped by the engine).  Needs a 16-byte aligned C with ldc % 8 == 0.
-  static const int env_dbg = [] { const char* e = getenv("OASR_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
-  p.debug = env_dbg;
   CUtensorMap tmC = {}, tmC2 = {};
   static const int env_tma_c = [] { const char* e = getenv("OASR_GEMM_TMA_STORE"); return e ? atoi(e) : 1; }();
   const bool bf16_out = epilogue <= OASR_EPI_BF16_GELU_BWD;
