@@ -78,7 +78,7 @@ def linear_dgrad(dy: Tensor, w_bf16: Tensor, *, epi=K.EPI_BF16, aux=None, out=No
     return K.gemm(dy, w_bf16, M, Kd, N, b_mn=True, epi=epi, aux=aux, out=out, block_n=_pick_block_n(M, Kd))
 
 
-def linear_wgrad(dy: Tensor, x: Tensor, n_valid: Optional[int] = None):
+def linear_wgrad(dy: Tensor, x: Tensor, n_valid: Optional[int] = None, side=None):
     """dW (N, K) f32 = dy^T x.  Both operands are read MN-major straight from their (M, *) row-major storage
     (A = dy^T is "stored (K=M, M=N)", B = x is "stored (K=M, N=K)"); split-K + fp32 red.add when the output has
     too few tiles to fill the GPU."""
@@ -89,9 +89,14 @@ def linear_wgrad(dy: Tensor, x: Tensor, n_valid: Optional[int] = None):
     tiles = math.ceil(N / 128) * math.ceil(Kd / bn)
     split = _pick_split_k(tiles, math.ceil(M / 64))
     dyv = dy if n_valid is None else dy[:, :n_valid]
-    out = None if split == 1 else torch.zeros((N, Kd), device=x.device, dtype=torch.float32)
-    return K.gemm(dyv, x, N, Kd, M, a_mn=True, b_mn=True, out=out,
-                  epi=K.EPI_F32 if out is None else K.EPI_F32_ATOMIC_ADD, split_k=split, block_n=bn)
+    alloc = torch.empty if split == 1 else torch.zeros     # allocated (and zeroed) on the caller's stream
+    out = alloc((N, Kd), device=x.device, dtype=torch.float32)
+
+    def launch():
+        return K.gemm(dyv, x, N, Kd, M, a_mn=True, b_mn=True, out=out,
+                      epi=K.EPI_F32 if split == 1 else K.EPI_F32_ATOMIC_ADD, split_k=split, block_n=bn)
+
+    return side.run(launch) if side is not None else launch()
 
 
 class _ZeroPool:
@@ -111,9 +116,11 @@ class _ZeroPool:
         return v
 
 
-def bias_grad(dy: Tensor, n: Optional[int] = None, pool: Optional[_ZeroPool] = None) -> Tensor:
+def bias_grad(dy: Tensor, n: Optional[int] = None, pool: Optional[_ZeroPool] = None, side=None) -> Tensor:
     n = dy.shape[1] if n is None else n
     db = pool.take(n) if pool is not None else torch.zeros(n, device=dy.device, dtype=torch.float32)
+    if side is not None:
+        return side.run(lambda: K.colsum_(dy, db, n))
     return K.colsum_(dy, db, n)
 
 
@@ -137,20 +144,16 @@ class _Side:
             self.side = _side_streams[idx]
             self.main = torch.cuda.current_stream(idx)
 
-    def run(self, fn, *keep):
-        """fn() on the side stream, after everything enqueued on the main stream so far.  `keep`: main-stream tensors
-        fn reads that may be released before join() (none today: locals live until backward returns)."""
+    def run(self, fn):
+        """fn() on the side stream, after everything enqueued on the main stream so far.  fn must only LAUNCH: every
+        tensor it touches is allocated by the caller on the main stream (whose pool the caching allocator then keeps
+        ordered with the main stream; the side stream's accesses sit between wait_stream and join), so no
+        record_stream bookkeeping -- and no cross-pool churn -- is needed."""
         if not self.on:
             return fn()
         self.side.wait_stream(self.main)
         with torch.cuda.stream(self.side):
-            out = fn()
-        for t in keep:
-            t.record_stream(self.side)
-        for t in (out if isinstance(out, (tuple, list)) else (out,)):
-            if isinstance(t, Tensor):
-                t.record_stream(self.main)   # allocated from the side stream's pool, consumed on the main stream
-        return out
+            return fn()
 
     def join(self):
         if self.on:
@@ -313,6 +316,11 @@ class _BlockFn(torch.autograd.Function):
         H = blk.attn.n_head
         d = x.shape[1]
         sh = blk._shadows()
+        side = _Side(x.device)
+        kvc = None
+        if xa is not None:   # the cross-attention K/V projection only needs the encoder output: side stream, joined below
+            kvc = torch.empty((xa.shape[0], 2 * d), device=x.device, dtype=torch.bfloat16)
+            side.run(lambda: linear_fwd(xa, sh["wckv"], sh["bckv"], out=kvc))
         ln1, mean1, rstd1 = K.layernorm_fwd(x, blk.attn_ln.weight, blk.attn_ln.bias)
         qkv = linear_fwd(ln1, sh["wqkv"], sh["bqkv"])
         ao, lse = K.attention_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], B, H, T, T, causal=causal, kv_len=kv_len)
@@ -321,7 +329,7 @@ class _BlockFn(torch.autograd.Function):
         if xa is not None:
             lnc, meanc, rstdc = K.layernorm_fwd(x1, blk.cross_attn_ln.weight, blk.cross_attn_ln.bias)
             qc = linear_fwd(lnc, sh["wcq"], blk.cross_attn.query.bias)
-            kvc = linear_fwd(xa, sh["wckv"], sh["bckv"])
+            side.join()
             co, lsec = K.attention_fwd(qc, kvc[:, :d], kvc[:, d:], B, H, T, Ta)
             x2 = linear_fwd(co, sh["wco"], blk.cross_attn.out.bias, epi=K.EPI_BF16_RESIDUAL, aux=x1)
             saved += [xa, meanc, rstdc, lnc, qc, kvc, co, lsec, x2]
@@ -358,13 +366,11 @@ class _BlockFn(torch.autograd.Function):
 
         # ---- MLP: x3 = x2 + fc2(gelu(fc1(ln(x2))))
         side = _Side(dev)
-        if side.on:
-            pool.buf.record_stream(side.side)
-        grads["mlp.2.weight"] = side.run(lambda: linear_wgrad(dx3, g))
-        grads["mlp.2.bias"] = side.run(lambda: bias_grad(dx3, pool=pool))
+        grads["mlp.2.weight"] = linear_wgrad(dx3, g, side=side)
+        grads["mlp.2.bias"] = bias_grad(dx3, pool=pool, side=side)
         dh = linear_dgrad(dx3, sh["w2"], epi=K.EPI_BF16_GELU_BWD, aux=h)
-        grads["mlp.0.weight"] = side.run(lambda: linear_wgrad(dh, ln2))
-        grads["mlp.0.bias"] = side.run(lambda: bias_grad(dh, pool=pool))
+        grads["mlp.0.weight"] = linear_wgrad(dh, ln2, side=side)
+        grads["mlp.0.bias"] = bias_grad(dh, pool=pool, side=side)
         dln2 = linear_dgrad(dh, sh["w1"])
         grads["mlp_ln.weight"], grads["mlp_ln.bias"] = z(d), z(d)
         dx2 = K.layernorm_bwd(dln2, x2, blk.mlp_ln.weight, mean2, rstd2, grads["mlp_ln.weight"], grads["mlp_ln.bias"],
@@ -372,18 +378,19 @@ class _BlockFn(torch.autograd.Function):
         dxa = None
         if cross:
             # ---- cross attention: x2 = x1 + out(attn(q(ln(x1)), kv(xa)))
-            grads["cross_attn.out.weight"] = side.run(lambda: linear_wgrad(dx2, co))
-            grads["cross_attn.out.bias"] = side.run(lambda: bias_grad(dx2, pool=pool))
+            grads["cross_attn.out.weight"] = linear_wgrad(dx2, co, side=side)
+            grads["cross_attn.out.bias"] = bias_grad(dx2, pool=pool, side=side)
             dco = linear_dgrad(dx2, sh["wco"])
             dqc = torch.empty_like(qc)
             dkvc = torch.empty_like(kvc)
             K.attention_bwd(qc, kvc[:, :d], kvc[:, d:], co, dco, lsec, B, H, T, Ta, dq=dqc, dk=dkvc[:, :d], dv=dkvc[:, d:])
-            grads["cross_attn.query.weight"] = side.run(lambda: linear_wgrad(dqc, lnc))
-            grads["cross_attn.query.bias"] = side.run(lambda: bias_grad(dqc, pool=pool))
-            dwkv = side.run(lambda: linear_wgrad(dkvc, xa))
+            grads["cross_attn.query.weight"] = linear_wgrad(dqc, lnc, side=side)
+            grads["cross_attn.query.bias"] = bias_grad(dqc, pool=pool, side=side)
+            dwkv = linear_wgrad(dkvc, xa, side=side)
             grads["cross_attn.key.weight"], grads["cross_attn.value.weight"] = dwkv[:d], dwkv[d:]
-            grads["cross_attn.value.bias"] = side.run(lambda: bias_grad(dkvc, pool=pool))[d:]
-            dxa = linear_dgrad(dkvc, sh["wckv"])
+            grads["cross_attn.value.bias"] = bias_grad(dkvc, pool=pool, side=side)[d:]
+            dxa = torch.empty_like(xa)   # only the encoder's backward reads it
+            side.run(lambda: linear_dgrad(dkvc, sh["wckv"], out=dxa))
             dlnc = linear_dgrad(dqc, sh["wcq"])
             grads["cross_attn_ln.weight"], grads["cross_attn_ln.bias"] = z(d), z(d)
             dx1 = K.layernorm_bwd(dlnc, x1, blk.cross_attn_ln.weight, meanc, rstdc, grads["cross_attn_ln.weight"],
@@ -391,15 +398,15 @@ class _BlockFn(torch.autograd.Function):
         else:
             dx1 = dx2
         # ---- self attention: x1 = x + out(attn(qkv(ln(x))))
-        grads["attn.out.weight"] = side.run(lambda: linear_wgrad(dx1, ao))
-        grads["attn.out.bias"] = side.run(lambda: bias_grad(dx1, pool=pool))
+        grads["attn.out.weight"] = linear_wgrad(dx1, ao, side=side)
+        grads["attn.out.bias"] = bias_grad(dx1, pool=pool, side=side)
         dao = linear_dgrad(dx1, sh["wo"])
         dqkv = torch.empty_like(qkv)
         K.attention_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], ao, dao, lse, B, H, T, T, causal=causal, kv_len=kv_len,
                         dq=dqkv[:, :d], dk=dqkv[:, d:2 * d], dv=dqkv[:, 2 * d:])
-        dw = side.run(lambda: linear_wgrad(dqkv, ln1))
+        dw = linear_wgrad(dqkv, ln1, side=side)
         grads["attn.query.weight"], grads["attn.key.weight"], grads["attn.value.weight"] = dw[:d], dw[d:2 * d], dw[2 * d:]
-        db = side.run(lambda: bias_grad(dqkv, pool=pool))
+        db = bias_grad(dqkv, pool=pool, side=side)
         grads["attn.query.bias"], grads["attn.value.bias"] = db[:d], db[2 * d:]
         dln1 = linear_dgrad(dqkv, sh["wqkv"])
         grads["attn_ln.weight"], grads["attn_ln.bias"] = z(d), z(d)
