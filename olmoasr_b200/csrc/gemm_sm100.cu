@@ -9,6 +9,8 @@
 //   warp 2       TMEM allocator / deallocator
 //   warps 4..11  epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 (one output row per thread) and the column
 //                half (w-4)/4 of the tile
+// CLUSTER = 4 (opt-in, OASR_GEMM_CLUSTER=4): two such pairs stacked along M; CTAs h and h + 2 hold the same half of the
+// B tile, each fetches a quarter and multicasts it to both; a slot's empty barrier collects both pairs' commits.
 // CLUSTER = 2: two CTAs (an SM pair) compute a 256 x BN tile with ONE tcgen05.mma.cta_group::2 stream issued by the
 // leader CTA: each CTA holds its 128 rows of A and its BN/2 rows of B in its own shared memory, so per flop the
 // tensor core reads half as much smem and TMA writes half as much (the 1-CTA 128 x 256 tile needs 96 B/clk of operand
@@ -23,6 +25,7 @@
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 
+#include <stdio.h>
 #include <stdlib.h>
 
 namespace oasr {
@@ -48,14 +51,15 @@ struct GemmParams {
   int tma_c;     // 1: bf16 outputs leave through the staging buffers + TMA stores (tmC / tmC2 are valid)
 };
 
-template <int BN, int CLUSTER = 1>
+template <int BN, int CLUSTER = 1, int EW = 8>
 struct Cfg {
-  static constexpr int B_STAGE_BYTES = (BN / CLUSTER) * BK * 2;   // per CTA
+  static constexpr int B_STAGE_BYTES = (BN / (CLUSTER >= 2 ? 2 : 1)) * BK * 2;   // per CTA (a pair splits B in two)
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   // bf16 epilogues of the 128/256-wide tiles leave through shared memory: two 32-row x 128-byte staging buffers per
   // epilogue warp, drained by TMA bulk stores (a per-thread 16-byte store touches 32 lines per warp instruction --
   // 4096 LSU wavefronts per tile and output, which bounded the K = 1024 GEMMs)
-  static constexpr int STG_BYTES = (BN >= 128) ? 8 * 2 * 4096 : 0;
+  static constexpr int STG_BYTES = (BN >= 128) ? 65536 : 0;
+  static constexpr int SLOTS = 65536 / (EW * 2048);               // 2 KB staging slots per epilogue warp (4 or 2)
   static constexpr int TAIL_BYTES = 2 * BN * 4 + 256;             // bias staging + mbarriers + TMEM slot
   static constexpr int BUDGET = 232448 - TAIL_BYTES - STG_BYTES;
   static constexpr int STAGES = (BUDGET / STAGE_BYTES) > 8 ? 8 : (BUDGET / STAGE_BYTES);
@@ -108,13 +112,19 @@ __device__ __forceinline__ void decode_tile(int tile, const GemmParams& p, int t
   m_blk = mc * cluster + cta_rank;
 }
 
-template <int BN, int A_MN, int B_MN, int CLUSTER>
-__global__ void __launch_bounds__(384, 1)
+template <int BN, int A_MN, int B_MN, int CLUSTER, int EW>
+__global__ void __launch_bounds__(128 + 32 * EW, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
                     const GemmParams p) {
-  using C = Cfg<BN, CLUSTER>;
+  using C = Cfg<BN, CLUSTER, EW>;
   constexpr int STAGES = C::STAGES;
+  constexpr int PAIRW = CLUSTER >= 2 ? 2 : 1;                      // CTAs per MMA (cta_group)
+  constexpr int NPAIR = CLUSTER / PAIRW;                          // MMA streams per cluster (CLUSTER = 4: two pairs share B)
+  constexpr int CQ = EW / 4;                                      // column groups (4 warps = 128 TMEM lanes each)
+  constexpr int ACT = (BN / 32 < CQ) ? BN / 32 : CQ;              // groups that own at least one 32-column chunk
+  constexpr int NCH = BN / (32 * ACT);                            // chunks per epilogue warp
+  constexpr int SLOTS = C::SLOTS;
 
   // all shared memory is dynamic so that the 128B-swizzled regions start on a 1024-byte boundary without slack:
   //   [STAGES x (A | B)] [8 warps x 2 x 4 KB output staging] [bias 2 x BN f32] [mbarriers] [TMEM slot]
@@ -144,11 +154,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bar_full[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bar_empty[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bar_empty[s]), NPAIR);   // one commit per MMA stream that reads this slot's B
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bar_tmem_full[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bar_tmem_empty[s]), 8 * CLUSTER);  // one arrive per epilogue warp of the pair
+      ptx::mbar_init(ptx::smem_u32(&bar_tmem_empty[s]), 4 * ACT * PAIRW);  // one arrive per active epilogue warp of the pair
     }
     ptx::fence_barrier_init();
   }
@@ -166,6 +176,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (CLUSTER > 1) ptx::cluster_sync();  // peer barriers are initialised before any remote signal
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  if (EW == 16) {   // 640 threads start at 96 registers; the control warpgroup hands 32 each to the 16 epilogue warps
+    if (warp < 4) ptx::setmaxnreg_dec<64>(); else ptx::setmaxnreg_inc<104>();
+  }
 
   // tile walk: with CLUSTER = 2 the pair (2*pm, 2*pm+1) of M tiles shares n_blk; both CTAs see the same sequence
   const uint32_t cta_rank = (CLUSTER > 1) ? ptx::cluster_ctarank() : 0;
@@ -173,7 +186,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int num_tiles = tiles_mc * p.tiles_n * p.splits;
   const int tile0 = blockIdx.x / CLUSTER;
   const int tile_step = gridDim.x / CLUSTER;
-  constexpr uint16_t kMask = (1u << CLUSTER) - 1;
+  constexpr uint16_t kMask = (1u << CLUSTER) - 1;                 // every CTA whose smem slot the commit frees
+  const uint16_t pair_mask = static_cast<uint16_t>(0x3u << (cta_rank & ~1u));   // this CTA's MMA pair
 
   if (warp == 0) {
     // ===================== TMA producer (warp-convergent loop, one elected lane issues) =====================
@@ -208,9 +222,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               ptx::tma_load_2d(sb, &tmB, full, kb * BK, n_blk * BN);
             }
           } else {
-            // both CTAs fill their own smem; every byte is accounted on the LEADER's full barrier
+            // both CTAs fill their own smem; every byte is accounted on the pair LEADER's full barrier
             const uint32_t full = ptx::smem_u32(&bar_full[stage]) & ptx::kPeerBitMask;
-            if (cta_rank == 0) ptx::mbar_arrive_expect_tx(full, CLUSTER * C::STAGE_BYTES);
+            if ((cta_rank & 1) == 0) ptx::mbar_arrive_expect_tx(full, PAIRW * C::STAGE_BYTES);
             if (A_MN) {
 #pragma unroll
               for (int i = 0; i < BM / 64; ++i)
@@ -218,12 +232,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             } else {
               ptx::tma_load_2d_2sm(sa, &tmA, full, kb * BK, m_blk * BM);
             }
-            if (B_MN) {   // this CTA's BN/2 columns of B: BN/128 chunks of 64
+            const int h = cta_rank & 1;            // which half of the B tile this CTA's MMA operand is
+            if (NPAIR == 1) {
+              if (B_MN) {   // this CTA's BN/2 columns of B: BN/128 chunks of 64
 #pragma unroll
-              for (int i = 0; i < BN / 128; ++i)
-                ptx::tma_load_2d_2sm(sb + i * (BK * 128), &tmB, full, n_blk * BN + (cta_rank * (BN / 128) + i) * 64, kb * BK);
-            } else {      // this CTA's BN/2 rows of B
-              ptx::tma_load_2d_2sm(sb, &tmB, full, kb * BK, n_blk * BN + cta_rank * (BN / 2));
+                for (int i = 0; i < BN / 128; ++i)
+                  ptx::tma_load_2d_2sm(sb + i * (BK * 128), &tmB, full, n_blk * BN + (h * (BN / 128) + i) * 64, kb * BK);
+              } else {      // this CTA's BN/2 rows of B
+                ptx::tma_load_2d_2sm(sb, &tmB, full, kb * BK, n_blk * BN + h * (BN / 2));
+              }
+            } else {
+              // two pairs stacked along M use the same B tile: CTAs h and h + 2 hold identical halves, each fetches
+              // one quarter and multicasts it to both (halves the L2 -> SM traffic of B)
+              const int pr = cta_rank >> 1;
+              const uint16_t mc = static_cast<uint16_t>((1u << h) | (1u << (h + 2)));
+              if (B_MN) {   // BN = 256: this half is two 64-column chunks, one per pair
+                ptx::tma_load_2d_2sm_mc(sb + pr * (BK * 128), &tmB, full, n_blk * BN + (h * 2 + pr) * 64, kb * BK, mc);
+              } else {      // BN/4 rows (8-row swizzle atoms stay aligned: BN/4 * 128 B is a multiple of 1024)
+                ptx::tma_load_2d_2sm_mc(sb + pr * (BN / 4) * 128, &tmB, full, kb * BK, n_blk * BN + h * (BN / 2) + pr * (BN / 4), mc);
+              }
             }
           }
           }
@@ -236,8 +263,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ===================== MMA issuer (leader CTA only when paired) =====================
     // The whole warp runs the loop (all lanes wait on the barriers); elect.sync picks the issuing lane so that the
     // descriptor arithmetic and the UTCHMMAs stay on the uniform datapath.
-    if (cta_rank == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM * CLUSTER, BN, A_MN, B_MN);
+    if ((cta_rank & 1) == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM * PAIRW, BN, A_MN, B_MN);
       // K-major  : 8-row groups 1024 B apart (SBO); LBO unused for swizzled K-major (CUTLASS sets 1)
       // MN-major : 64-element MN chunks BK*128 B apart (LBO); 8-k groups 1024 B apart (SBO)
       constexpr uint32_t a_lbo = A_MN ? BK * 128 : 16, a_sbo = 1024;
@@ -274,7 +301,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             else ptx::tc_commit2_mc(ptx::smem_u32(&bar_empty[stage]), kMask);
             if (kb + 1 == kb1) {   // accumulator complete (each CTA's epilogue drains its own 128 rows)
               if (CLUSTER == 1) ptx::tc_commit(ptx::smem_u32(&bar_tmem_full[acc]));
-              else ptx::tc_commit2_mc(ptx::smem_u32(&bar_tmem_full[acc]), kMask);
+              else ptx::tc_commit2_mc(ptx::smem_u32(&bar_tmem_full[acc]), pair_mask);
             }
           }
           __syncwarp();
@@ -283,10 +310,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && ((warp - 4) >> 2) < ACT) {
     // ===================== epilogue =====================
     const int q = warp & 3;            // TMEM lane quarter this warp may touch
-    const int chalf = (warp - 4) >> 2; // which half of the tile's columns this warp drains
+    const int chalf = (warp - 4) >> 2; // which group of the tile's columns this warp drains
     const int etid = threadIdx.x - 128;
     const int row_in_tile = q * 32 + lane;
     int acc = 0;
@@ -299,7 +326,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // this warp's staging area: four 2 KB slots, each one 32-row x 32-column bf16 chunk (64-byte rows, 64B swizzle).
     // A chunk is handed to the TMA engine as soon as it is staged, and a slot is refilled two (GELU: o1 in slots 0/1,
     // o2 in slots 2/3) or four chunks later, so the drain latency of the bulk store is never waited for.
-    const uint32_t stg = smem_base + STAGES * C::STAGE_BYTES + (warp - 4) * 8192;
+    const uint32_t stg = smem_base + STAGES * C::STAGE_BYTES + (warp - 4) * (SLOTS * 2048);
     uint32_t slotc = 0;   // chunks staged so far by this warp
     // residual / pre-activation chunks come in through the same slots: coalesced 16-byte LDGSTS (8 rows x 64 B per
     // warp instruction instead of 32 partial lines), then each thread reads its own row back
@@ -310,16 +337,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int row = m_blk * BM + row_in_tile;
       const bool row_ok = row < p.M;
       if (p.bias != nullptr) {  // stage this tile's bias once (rounded to bf16 like bias.to(x.dtype) unless fp32 output)
-        for (int i = etid; i < BN; i += 256) {
+        for (int i = etid; i < BN; i += 128 * ACT) {
           const int col = n_blk * BN + i;
           const float b = col < p.N ? __ldg(p.bias + col) : 0.f;
           s_bias[acc][i] = c_is_f32 ? b : bf16_round(b);
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // epilogue warps only
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * ACT) : "memory");  // active epilogue warps only
       }
       // aux (residual / pre-activation) rows of this thread, fetched before the accumulator is ready so that the
       // ~1 us global-load latency hides behind the MMAs (it used to be the top stall of the residual epilogue)
-      constexpr int NCH = BN / 64;   // 32-column chunks per epilogue warp (1, 2 or 4)
       auto issue_aux = [&](int ci, uint32_t buf) {   // aux columns of chunk ci of this warp -> slot `buf` (swizzled)
         const int u = lane & 3, r0 = lane >> 2;
         const int colu = n_blk * BN + (chalf * NCH + ci) * 32 + u * 8;
@@ -334,10 +360,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         ptx::cp_async_commit();
       };
-      if (aux_stage) {   // first chunk's aux travels while the accumulator is still being computed
-        if (lane == 0) ptx::tma_store_wait_read<3>();
+      constexpr int PRE = (SLOTS == 2) ? NCH : 1;   // chunks whose aux is requested before the accumulator is ready
+      static_assert(PRE <= SLOTS, "aux prefetch depth");
+      if (aux_stage) {   // aux travels while the accumulator is still being computed
+        if (lane == 0) ptx::tma_store_wait_read<SLOTS - PRE>();   // slot of chunk k is free once store k - SLOTS was read
         __syncwarp();
-        issue_aux(0, stg + (slotc & 3u) * 2048u);
+#pragma unroll
+        for (int j = 0; j < PRE; ++j)
+          if (n_blk * BN + (chalf * NCH + j) * 32 < p.N) issue_aux(j, stg + ((slotc + j) % SLOTS) * 2048u);
       } else if (use_aux && row_ok) {   // direct path: pull this thread's aux bytes towards L2
 #pragma unroll
         for (int ci = 0; ci < NCH; ++ci) {
@@ -522,22 +552,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
-template <int BN, int A_MN, int B_MN, int CLUSTER>
+template <int BN, int A_MN, int B_MN, int CLUSTER, int EW>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC2,
            const GemmParams& p, cudaStream_t st) {
-  using C = Cfg<BN, CLUSTER>;
-  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, CLUSTER>;
+  using C = Cfg<BN, CLUSTER, EW>;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, CLUSTER, EW>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     OASR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   const int tiles = ((p.tiles_m + CLUSTER - 1) / CLUSTER) * p.tiles_n * p.splits;  // cluster tiles
-  const int max_clusters = num_sms() / CLUSTER;
-  const int grid = (tiles < max_clusters ? tiles : max_clusters) * CLUSTER;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(384);
+  cfg.blockDim = dim3(128 + 32 * EW);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -547,17 +574,34 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  // persistent grid = the clusters that are co-resident (a GPC whose SM count is not a multiple of the cluster size
+  // cannot host one on its leftover SMs, so this can be fewer than num_sms / CLUSTER)
+  static int max_clusters = 0;  // per instantiation
+  if (max_clusters == 0) {
+    int n = 0;
+    cfg.gridDim = dim3(num_sms() / CLUSTER * CLUSTER);
+    if (CLUSTER > 1 && cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0)
+      max_clusters = n < num_sms() / CLUSTER ? n : num_sms() / CLUSTER;
+    else
+      max_clusters = num_sms() / CLUSTER;
+    (void)cudaGetLastError();
+    if (getenv("OASR_GEMM_VERBOSE"))
+      fprintf(stderr, "oasr gemm<BN=%d,cluster=%d>: %d co-resident clusters (occupancy query %d), %d stages\n", BN, CLUSTER,
+              max_clusters, n, C::STAGES);
+  }
+  const int grid = (tiles < max_clusters ? tiles : max_clusters) * CLUSTER;
+  cfg.gridDim = dim3(grid);
   OASR_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmC2, p));
   return OASR_OK;
 }
 
-template <int BN, int CLUSTER>
+template <int BN, int CLUSTER, int EW>
 int dispatch_major(int a_mn, int b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                    const CUtensorMap& tmC2, const GemmParams& p, cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch<BN, 0, 0, CLUSTER>(tmA, tmB, tmC, tmC2, p, st);
-  if (!a_mn && b_mn) return launch<BN, 0, 1, CLUSTER>(tmA, tmB, tmC, tmC2, p, st);
-  if (a_mn && b_mn) return launch<BN, 1, 1, CLUSTER>(tmA, tmB, tmC, tmC2, p, st);
-  return launch<BN, 1, 0, CLUSTER>(tmA, tmB, tmC, tmC2, p, st);
+  if (!a_mn && !b_mn) return launch<BN, 0, 0, CLUSTER, EW>(tmA, tmB, tmC, tmC2, p, st);
+  if (!a_mn && b_mn) return launch<BN, 0, 1, CLUSTER, EW>(tmA, tmB, tmC, tmC2, p, st);
+  if (a_mn && b_mn) return launch<BN, 1, 1, CLUSTER, EW>(tmA, tmB, tmC, tmC2, p, st);
+  return launch<BN, 1, 0, CLUSTER, EW>(tmA, tmB, tmC, tmC2, p, st);
 }
 
 }  // namespace
@@ -604,10 +648,17 @@ extern "C" int oasr_gemm_bf16(const void* A, int64_t lda, int a_layout, const vo
   else
     rc = make_tmap_2d(&tmA, A, 2, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64, BK, true);
   if (rc) return rc;
-  static const int env_cluster0 = [] { const char* e = getenv("OASR_GEMM_CLUSTER"); return e ? atoi(e) : 2; }();
-  const bool pair0 = env_cluster0 >= 2 && p.tiles_m >= 2 && block_n >= 128;
-  if (b_layout == OASR_K_MAJOR)  // paired CTAs each fetch (and multicast) half of the B tile's rows
-    rc = make_tmap_2d(&tmB, B, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BK, pair0 ? block_n / 2 : block_n, true);
+  // cluster shape: 4 = two CTA pairs stacked along M that share (multicast) the B tile, 2 = one CTA pair, 1 = single CTA.
+  // OASR_GEMM_CLUSTER caps it (read per call so that tools/ab_step.py can alternate in-process).  Default 2: the
+  // 4-CTA shape moves 25 % fewer operand bytes from L2 and is ~9 % faster per SM, but only 33 such clusters are
+  // co-resident on a B200 (132 of 148 SMs; GPCs with an odd TPC count strand one TPC each), and the whole training
+  // step measured 203.4 ms against 201.9 ms for pairs (profiles/r01_ab_gemm_cluster.txt).
+  const int env_cluster = [] { const char* e = getenv("OASR_GEMM_CLUSTER"); return e ? atoi(e) : 2; }();
+  int cluster = 1;
+  if (env_cluster >= 2 && p.tiles_m >= 2 && block_n >= 128) cluster = 2;
+  if (env_cluster >= 4 && p.tiles_m >= 4 && block_n == 256) cluster = 4;
+  if (b_layout == OASR_K_MAJOR)  // a CTA fetches its share of the B tile's rows: all / half (pair) / quarter (two pairs)
+    rc = make_tmap_2d(&tmB, B, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, BK, block_n / cluster, true);
   else
     rc = make_tmap_2d(&tmB, B, 2, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, BK, true);
   if (rc) return rc;
@@ -629,14 +680,17 @@ extern "C" int oasr_gemm_bf16(const void* A, int64_t lda, int a_layout, const vo
   }
 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  // CTA pairs need >= 2 M tiles and a B tile that splits in two; OASR_GEMM_CLUSTER=1 selects the 1-CTA kernel (A/B tests)
-  static const int env_cluster = [] { const char* e = getenv("OASR_GEMM_CLUSTER"); return e ? atoi(e) : 2; }();
-  const bool pair = env_cluster >= 2 && p.tiles_m >= 2 && block_n >= 128;
+#define OASR_GEMM_DISPATCH(BNv, CLv) return dispatch_major<BNv, CLv, 8>(a_layout, b_layout, tmA, tmB, tmC, tmC2, p, st)
   switch (block_n) {
-    case 256: return pair ? dispatch_major<256, 2>(a_layout, b_layout, tmA, tmB, tmC, tmC2, p, st)
-                          : dispatch_major<256, 1>(a_layout, b_layout, tmA, tmB, tmC, tmC2, p, st);
-    case 128: return pair ? dispatch_major<128, 2>(a_layout, b_layout, tmA, tmB, tmC, tmC2, p, st)
-                          : dispatch_major<128, 1>(a_layout, b_layout, tmA, tmB, tmC, tmC2, p, st);
-    default: return dispatch_major<64, 1>(a_layout, b_layout, tmA, tmB, tmC, tmC2, p, st);
+    case 256:
+      if (cluster == 4) OASR_GEMM_DISPATCH(256, 4);
+      if (cluster == 2) OASR_GEMM_DISPATCH(256, 2);
+      OASR_GEMM_DISPATCH(256, 1);
+    case 128:
+      if (cluster == 2) OASR_GEMM_DISPATCH(128, 2);
+      OASR_GEMM_DISPATCH(128, 1);
+    default:
+      OASR_GEMM_DISPATCH(64, 1);
   }
+#undef OASR_GEMM_DISPATCH
 }

@@ -17,6 +17,7 @@ def main():
     ap.add_argument("--epi", default="bf16")
     ap.add_argument("--a-mn", action="store_true"); ap.add_argument("--b-mn", action="store_true")
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--seconds", type=float, default=0.0, help="loop for this long and report SM clock / power (nvidia-smi)")
     args = ap.parse_args()
     from olmoasr_b200 import kernels as K
     dev = torch.device("cuda", 0)
@@ -43,6 +44,24 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.iters
+    if args.seconds > 0:
+        import subprocess
+        import time
+        n = max(1, int(args.seconds * 1e3 / ms))
+        pr = subprocess.Popen(["nvidia-smi", "--query-gpu=clocks.sm,power.draw", "--format=csv,noheader,nounits", "-lms", "100", "-i", "0"],
+                              stdout=subprocess.PIPE, text=True)
+        e0.record()
+        for _ in range(n):
+            K.gemm(a, b, M, N, Kd, **kw)
+        e1.record()
+        torch.cuda.synchronize()
+        pr.terminate()
+        rows = [ln.split(",") for ln in pr.stdout.read().strip().splitlines()]
+        rows = rows[len(rows) // 3:]   # steady state
+        clk = sorted(float(r[0]) for r in rows)
+        pw = sorted(float(r[1]) for r in rows)
+        ms = e0.elapsed_time(e1) / n
+        print(f"   sustained {args.seconds:.0f} s: sm clock median {clk[len(clk) // 2]:.0f} MHz, power median {pw[len(pw) // 2]:.0f} W, ", end="")
     print(f"M={M} N={N} K={Kd} epi={args.epi} a_mn={args.a_mn} b_mn={args.b_mn}: {ms:.4f} ms  {2.0 * M * N * Kd / ms / 1e9:.1f} TFLOP/s")
 
 
