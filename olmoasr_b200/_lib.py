@@ -11,7 +11,9 @@ from pathlib import Path
 
 import torch
 
-_LIB_PATH = Path(__file__).resolve().parent / "csrc" / "liboasr_b200.so"
+# OASR_B200_LIB points at an alternative build of the same library (A/B measurements of kernel variants); it must
+# export the same ABI -- there is still no non-CUDA fallback.
+_LIB_PATH = Path(os.environ.get("OASR_B200_LIB") or Path(__file__).resolve().parent / "csrc" / "liboasr_b200.so")
 _lib = None
 
 c_void_p = ctypes.c_void_p
