@@ -163,7 +163,15 @@ class _Side:
 def kv_len_from_padding_mask(padding_mask: Tensor) -> Tensor:
     """The reference passes a dense additive mask (B, 448, 448) whose columns >= len(text_input) are -inf for every
     row (scripts/training/train_timestamps.py:314-315).  The kernels take that as a per-sample key count."""
-    return (padding_mask[:, 0, :] == 0).sum(dim=-1).to(torch.int32)
+    cached = getattr(padding_mask, "_oasr_kv_len", None)   # computed once per decoder call, not once per block
+    if cached is not None and cached[0] == padding_mask._version:
+        return cached[1]
+    kv = (padding_mask[:, 0, :] == 0).sum(dim=-1).to(torch.int32)
+    try:
+        padding_mask._oasr_kv_len = (padding_mask._version, kv)   # rides on this tensor object; in-place edits invalidate
+    except (AttributeError, RuntimeError):
+        pass
+    return kv
 
 
 class _ShadowCache:
