@@ -39,6 +39,10 @@ extern "C" {
 OASR_API const char* oasr_last_error(void); /* thread-local, valid until the next failing call          */
 OASR_API int oasr_abi_version(void);
 OASR_API int oasr_device_sm_count(void);
+/* SMs the persistent GEMM may occupy (0 = all).  A persistent grid that does not fit next to a concurrent kernel
+ * (NCCL's all-reduce CTAs under DDP, train_timestamps.py:2330) runs its displaced CTAs as a second wave; leaving
+ * those SMs free avoids it.  Process-wide; returns the previous value. */
+OASR_API int oasr_gemm_set_sm_budget(int n_sms);
 
 /* ---- dense GEMM on tcgen05 / TMEM ---------------------------------------------------------------
  * Replaces F.linear in Linear.forward (olmoasr/model.py:97-101), its autograd dgrad / wgrad, the tied

@@ -101,3 +101,13 @@ int make_tmap_3d(CUtensorMap* out, const void* base, int elt_bytes, uint64_t d0,
 extern "C" const char* oasr_last_error(void) { return oasr::g_err; }
 extern "C" int oasr_abi_version(void) { return 1; }
 extern "C" int oasr_device_sm_count(void) { return oasr::num_sms(); }
+
+namespace oasr {
+static int g_gemm_sm_budget = 0;
+int gemm_sm_budget() { return (g_gemm_sm_budget > 0 && g_gemm_sm_budget < num_sms()) ? g_gemm_sm_budget : num_sms(); }
+}  // namespace oasr
+extern "C" int oasr_gemm_set_sm_budget(int n_sms) {
+  const int prev = oasr::g_gemm_sm_budget;
+  oasr::g_gemm_sm_budget = n_sms < 0 ? 0 : n_sms;
+  return prev;
+}

@@ -37,6 +37,7 @@ int num_sms();
 // 2-D bf16/f32 row-major tensor map: `inner` contiguous elements per row, `outer` rows,
 // `row_stride_bytes` between rows, box = box_inner x box_outer, 128-byte swizzle when
 // swizzle128 (box_inner * elt must then be 128 bytes).
+int gemm_sm_budget();   // SMs the persistent GEMM may occupy (oasr_gemm_set_sm_budget)
 int make_tmap_2d(CUtensorMap* out, const void* base, int elt_bytes, uint64_t inner, uint64_t outer,
                  uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, bool swizzle128);
 // swizzle_bytes: 0 (none), 64 or 128

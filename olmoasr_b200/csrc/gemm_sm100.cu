@@ -589,7 +589,10 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
       fprintf(stderr, "oasr gemm<BN=%d,cluster=%d>: %d co-resident clusters (occupancy query %d), %d stages\n", BN, CLUSTER,
               max_clusters, n, C::STAGES);
   }
-  const int grid = (tiles < max_clusters ? tiles : max_clusters) * CLUSTER;
+  int use_clusters = gemm_sm_budget() / CLUSTER;
+  if (use_clusters > max_clusters) use_clusters = max_clusters;
+  if (use_clusters < 1) use_clusters = 1;
+  const int grid = (tiles < use_clusters ? tiles : use_clusters) * CLUSTER;
   cfg.gridDim = dim3(grid);
   OASR_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmC2, p));
   return OASR_OK;

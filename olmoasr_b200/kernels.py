@@ -19,6 +19,12 @@ EPI_BF16, EPI_BF16_GELU, EPI_BF16_RESIDUAL, EPI_BF16_GELU_BWD, EPI_F32, EPI_F32_
 GEMM_PROFILE = None
 
 
+def set_gemm_sm_budget(n_sms: int) -> int:
+    """SMs the persistent GEMM may occupy (0 = all); returns the previous setting.  Under DDP the NCCL all-reduce
+    CTAs need SMs of their own: a persistent grid that no longer fits runs its displaced CTAs as a second wave."""
+    return _lib.lib().oasr_gemm_set_sm_budget(int(n_sms))
+
+
 def _req(cond, msg):
     if not cond:
         raise ValueError(msg)

@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--layers", type=int, default=0, help="truncate encoder/decoder depth (for ncu captures)")
     ap.add_argument("--gemm-table", action="store_true", help="per-shape GEMM time / TFLOP/s (CUDA events per launch)")
+    ap.add_argument("--serial", action="store_true", help="side stream off: per-kernel device times do not overlap")
     ap.add_argument("--no-profiler", action="store_true", help="just run the steps (when wrapped in ncu)")
     args = ap.parse_args()
     import olmoasr_b200 as ob
@@ -25,6 +26,9 @@ def main():
     from olmoasr_b200.model import OLMoASR
     from olmoasr_b200.optim import FusedAdamW
 
+    if args.serial:
+        from olmoasr_b200 import _core as _c
+        _c.SIDE_STREAM = False
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
     dims = ob.VARIANT_TO_DIMS[args.variant]
@@ -58,7 +62,9 @@ def main():
     t_all = (time.perf_counter() - t0) / 3
     print(f"# host enqueue time per step {t_enq * 1e3:.1f} ms; wall per step {t_all * 1e3:.1f} ms (CPU-bound if these are close)")
     if args.gemm_table:
+        from olmoasr_b200 import _core
         from olmoasr_b200 import kernels as K
+        _core.SIDE_STREAM = False   # serialise launches: a launch's event time must be its own duration
         K.GEMM_PROFILE = []
         step()
         torch.cuda.synchronize()
