@@ -47,6 +47,14 @@ def test_argument_validation_returns_error_codes_without_a_gpu():
         _lib.check(rc, "attention")
 
 
+def test_gemm_sm_budget_is_process_state_and_returns_the_previous_value():
+    from olmoasr_b200 import kernels as K
+
+    prev = K.set_gemm_sm_budget(132)
+    assert K.set_gemm_sm_budget(0) == 132
+    assert K.set_gemm_sm_budget(-5) == 0 and K.set_gemm_sm_budget(prev) == 0   # negative clamps to "all SMs"
+
+
 def test_product_package_never_imports_the_oracle():
     for path in (ROOT / "olmoasr_b200").rglob("*.py"):
         src = path.read_text()

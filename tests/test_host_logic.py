@@ -58,6 +58,23 @@ def test_kv_len_from_padding_mask():
     assert torch.equal(_core.kv_len_from_padding_mask(pm).long(), lens)
 
 
+def test_kv_len_is_cached_per_mask_object_and_invalidated_by_in_place_edits():
+    _, _, pm, lens = synthetic.text_batch(3)
+    a = _core.kv_len_from_padding_mask(pm)
+    assert _core.kv_len_from_padding_mask(pm) is a            # 24 decoder blocks share one computation
+    pm[0, :, 5:] = -float("inf")                               # in-place edit bumps the version counter
+    b = _core.kv_len_from_padding_mask(pm)
+    assert b is not a and int(b[0]) == 5 and torch.equal(b[1:].long(), lens[1:])
+    assert torch.equal(_core.kv_len_from_padding_mask(pm.clone()).long(), b.long())   # a new tensor recomputes
+
+
+def test_side_stream_helper_is_inert_off_cuda():
+    side = _core._Side(torch.device("cpu"))
+    assert not side.on
+    assert side.run(lambda: 41 + 1) == 42
+    side.join()
+
+
 def test_audio_helpers_match_oracle():
     assert np.array_equal(audio.mel_filterbank(80), logmel.mel_filters(80))
     x = np.arange(10, dtype=np.float32)
