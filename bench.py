@@ -210,7 +210,12 @@ def our_arm(args):
     with torch.device(dev):
         model = OLMoASR(dims)
     net = model
-    if world > 1:
+    reducer = None
+    ddp_impl = os.environ.get("OASR_DDP_IMPL", "torch")   # "blockwise": olmoasr_b200.ddp (opt-in until measured on NVLink)
+    if world > 1 and ddp_impl == "blockwise":
+        from olmoasr_b200.ddp import BlockwiseGradReducer
+        reducer = BlockwiseGradReducer(model)
+    elif world > 1:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], output_device=local_rank)
     opt = FusedAdamW(model.parameters(), lr=1.5e-3, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.1, max_grad_norm=1.0)
 
@@ -226,7 +231,10 @@ def our_arm(args):
         loss = net(mel, ti, pm, targets=ty)
         opt.zero_grad(set_to_none=True)
         loss.backward()
-        opt.step()
+        if reducer is not None:
+            opt.step(inv_scale=reducer.finish())
+        else:
+            opt.step()
         return loss
 
     def barrier():
@@ -298,6 +306,8 @@ def our_arm(args):
                                f"(BASELINE.json configs[2] at {world} GPU(s)): int16 waveform -> log-mel -> fwd/bwd -> CE -> "
                                f"{'NCCL all-reduce -> ' if world > 1 else ''}clip + AdamW",
                    "global_batch": global_batch, "parallelism": f"dp{world}",
+                   "grad_sync": ("none" if world == 1 else ("olmoasr_b200.ddp.BlockwiseGradReducer" if reducer is not None
+                                                            else "torch DistributedDataParallel")),
                    "l2": "no flush needed: per-step working set (~60 GB of activations at medium/32) is >> the 126 MB L2",
                    "loss": float(loss)},
         "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,

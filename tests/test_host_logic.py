@@ -176,3 +176,60 @@ def test_data_parallel_semantics_world2_gloo(tmp_path):
         w(x).pow(2).mean().backward()
         gs.append(w.weight.grad.clone())
     assert torch.allclose(r["grads"][0], (gs[0] + gs[1]) / 2, atol=1e-6)
+
+
+class _ToyBlock(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.attn = torch.nn.Linear(6, 6)
+        self.mlp = torch.nn.Linear(6, 6)
+        self._param_names = [n for n, _ in self.named_parameters()]
+
+    def forward(self, x):
+        return x + self.mlp(torch.tanh(self.attn(x)))
+
+
+def _blockwise_worker(rank, world, port, out):
+    from olmoasr_b200.ddp import BlockwiseGradReducer, default_buckets
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(rank)                      # different initial weights: the constructor must broadcast rank 0's
+    net = torch.nn.Sequential(_ToyBlock(), _ToyBlock(), torch.nn.Linear(6, 3))
+    unused = torch.nn.Parameter(torch.zeros(2))  # never receives a gradient: finish() must still terminate
+    net.register_parameter("unused", unused)
+    red = BlockwiseGradReducer(net)
+    assert [len(b) for b in default_buckets(net)] == [4, 4, 3]
+    results = []
+    for it in range(2):                          # two steps: the reducer re-arms itself
+        net.zero_grad(set_to_none=True)
+        x = torch.randn(5, 6, generator=torch.Generator().manual_seed(100 * it + rank))
+        net(x).pow(2).mean().backward()
+        inv = red.finish()
+        results.append([p.grad.clone() * inv for p in net.parameters() if p.grad is not None])
+    w0 = [p.detach().clone() for p in net.parameters()]
+    if rank == 0:
+        torch.save({"grads": results, "weights": w0}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_blockwise_grad_reducer_matches_ddp_averaging_world2_gloo(tmp_path):
+    out = str(tmp_path / "r0.pt")
+    mp.spawn(_blockwise_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    r = torch.load(out, weights_only=False)
+    # reference arithmetic on one process: average of the per-rank gradients, starting from rank 0's weights
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(_ToyBlock(), _ToyBlock(), torch.nn.Linear(6, 3))
+    net.register_parameter("unused", torch.nn.Parameter(torch.zeros(2)))
+    for a, b in zip(net.parameters(), r["weights"]):
+        assert torch.equal(a.detach(), b)
+    for it in range(2):
+        per_rank = []
+        for rank in range(2):
+            net.zero_grad(set_to_none=True)
+            x = torch.randn(5, 6, generator=torch.Generator().manual_seed(100 * it + rank))
+            net(x).pow(2).mean().backward()
+            per_rank.append([p.grad.clone() for p in net.parameters() if p.grad is not None])
+        for got, g0, g1 in zip(r["grads"][it], per_rank[0], per_rank[1]):
+            assert torch.allclose(got, (g0 + g1) / 2, atol=1e-6)
