@@ -1,14 +1,16 @@
 // Persistent, warp-specialised bf16 GEMM for sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma
-// (single-thread issue, fp32 accumulators in TMEM, double-buffered) -> tcgen05.ld epilogue.
+// (elected-lane issue, fp32 accumulators in TMEM, double-buffered) -> tcgen05.ld epilogue -> staged TMA stores.
 //
 //   D[M,N] = epi( sum_k A[m,k] B[n,k] )
 //
-// One CTA per SM, 384 threads:
-//   warp 0       TMA producer (one lane)
-//   warp 1       MMA issuer   (one lane)
+// One CTA per SM, 128 + 32 * EW threads (EW = 8 epilogue warps is the only instantiated value; 16 warps with
+// setmaxnreg-rebalanced registers measured no faster):
+//   warp 0       TMA producer (warp-convergent loop, elect.sync picks the issuing lane)
+//   warp 1       MMA issuer   (same)
 //   warp 2       TMEM allocator / deallocator
-//   warps 4..11  epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 (one output row per thread) and the column
-//                half (w-4)/4 of the tile
+//   warps 4..    epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 (one output row per thread) and the column
+//                group (w-4)/4 of the tile; bf16 outputs go through four 2 KB 64B-swizzled staging slots per warp to
+//                TMA bulk stores, residual / pre-activation tiles come in through the same slots by LDGSTS
 // CLUSTER = 4 (opt-in, OASR_GEMM_CLUSTER=4): two such pairs stacked along M; CTAs h and h + 2 hold the same half of the
 // B tile, each fetches a quarter and multicasts it to both; a slot's empty barrier collects both pairs' commits.
 // CLUSTER = 2: two CTAs (an SM pair) compute a 256 x BN tile with ONE tcgen05.mma.cta_group::2 stream issued by the
@@ -55,9 +57,9 @@ template <int BN, int CLUSTER = 1, int EW = 8>
 struct Cfg {
   static constexpr int B_STAGE_BYTES = (BN / (CLUSTER >= 2 ? 2 : 1)) * BK * 2;   // per CTA (a pair splits B in two)
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  // bf16 epilogues of the 128/256-wide tiles leave through shared memory: two 32-row x 128-byte staging buffers per
-  // epilogue warp, drained by TMA bulk stores (a per-thread 16-byte store touches 32 lines per warp instruction --
-  // 4096 LSU wavefronts per tile and output, which bounded the K = 1024 GEMMs)
+  // bf16 epilogues of the 128/256-wide tiles leave through shared memory: 64 KB of 32-row x 64-byte staging slots
+  // (SLOTS per epilogue warp), drained by TMA bulk stores (a per-thread 16-byte store touches 32 lines per warp
+  // instruction -- 4096 LSU wavefronts per tile and output, which bounded the K = 1024 GEMMs)
   static constexpr int STG_BYTES = (BN >= 128) ? 65536 : 0;
   static constexpr int SLOTS = 65536 / (EW * 2048);               // 2 KB staging slots per epilogue warp (4 or 2)
   static constexpr int TAIL_BYTES = 2 * BN * 4 + 256;             // bias staging + mbarriers + TMEM slot
