@@ -41,10 +41,13 @@ def default_buckets(model: nn.Module) -> List[List[nn.Parameter]]:
 
 
 class BlockwiseGradReducer:
-    def __init__(self, model: nn.Module, process_group=None, buckets: Optional[Sequence[Iterable[nn.Parameter]]] = None):
+    def __init__(self, model: nn.Module, process_group=None, buckets: Optional[Sequence[Iterable[nn.Parameter]]] = None,
+                 coalesce: bool = True):
         if not dist.is_initialized():
             raise RuntimeError("BlockwiseGradReducer needs an initialised process group")
         self.group = process_group
+        # torch.distributed._coalescing_manager is a private API: without it every tensor gets its own async all-reduce
+        self.coalesce = coalesce and hasattr(dist, "_coalescing_manager")
         self.world = dist.get_world_size(process_group)
         self.buckets = [list(b) for b in (buckets if buckets is not None else default_buckets(model))]
         self._left = [len(b) for b in self.buckets]
@@ -75,10 +78,13 @@ class BlockwiseGradReducer:
         self._launched[i] = True
         if not grads or self.world == 1:
             return
-        with dist._coalescing_manager(group=self.group, async_ops=True) as cm:
-            for g in grads:
-                dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
-        self._works.append(cm)
+        if self.coalesce:
+            with dist._coalescing_manager(group=self.group, async_ops=True) as cm:
+                for g in grads:
+                    dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
+            self._works.append(cm)
+        else:
+            self._works.extend(dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group, async_op=True) for g in grads)
 
     def finish(self) -> float:
         """Launch whatever did not complete through the hooks (parameters without a gradient this step), wait for every

@@ -189,7 +189,7 @@ class _ToyBlock(torch.nn.Module):
         return x + self.mlp(torch.tanh(self.attn(x)))
 
 
-def _blockwise_worker(rank, world, port, out):
+def _blockwise_worker(rank, world, port, out, coalesce):
     from olmoasr_b200.ddp import BlockwiseGradReducer, default_buckets
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -198,7 +198,7 @@ def _blockwise_worker(rank, world, port, out):
     net = torch.nn.Sequential(_ToyBlock(), _ToyBlock(), torch.nn.Linear(6, 3))
     unused = torch.nn.Parameter(torch.zeros(2))  # never receives a gradient: finish() must still terminate
     net.register_parameter("unused", unused)
-    red = BlockwiseGradReducer(net)
+    red = BlockwiseGradReducer(net, coalesce=coalesce)
     assert [len(b) for b in default_buckets(net)] == [4, 4, 3]
     results = []
     for it in range(2):                          # two steps: the reducer re-arms itself
@@ -214,9 +214,10 @@ def _blockwise_worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_blockwise_grad_reducer_matches_ddp_averaging_world2_gloo(tmp_path):
+@pytest.mark.parametrize("coalesce", [True, False])
+def test_blockwise_grad_reducer_matches_ddp_averaging_world2_gloo(tmp_path, coalesce):
     out = str(tmp_path / "r0.pt")
-    mp.spawn(_blockwise_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    mp.spawn(_blockwise_worker, args=(2, _free_port(), out, coalesce), nprocs=2, join=True)
     r = torch.load(out, weights_only=False)
     # reference arithmetic on one process: average of the per-rank gradients, starting from rank 0's weights
     torch.manual_seed(0)
