@@ -1,12 +1,12 @@
-"""The same training step written with stock PyTorch ops only (nn.Linear / Conv1d / F.layer_norm /
-F.scaled_dot_product_attention with the reference's dense float mask / F.cross_entropy on fp32 logits / fused AdamW),
-under torch.autocast(bf16) -- i.e. what running the reference's model code on this GPU costs (last row).
-Independent of oracle/ and of olmoasr_b200's kernels; architecture per olmoasr/model.py:445-528,560-602,688-775.
+"""The reference's GPU path: the same training step written with stock PyTorch ops only (nn.Linear / Conv1d /
+F.layer_norm in fp32 / F.scaled_dot_product_attention with the reference's dense float mask / F.cross_entropy on fp32
+logits / clip_grad_norm_ / fused torch AdamW / DistributedDataParallel), under torch.autocast(bf16) -- i.e. what running
+the reference's model code (olmoasr/model.py:445-528,560-602,688-775 under scripts/training/train_timestamps.py:1414,
+1440-1454,1508-1522,2330) costs on this GPU with cuBLASLt / cuDNN / ATen SDPA.  SURVEY 8(d) last row: the number the
+headline has to beat.  Independent of oracle/ and of olmoasr_b200's kernels (it only borrows the synthetic batch and the
+mel filterbank table); `bench.py` reports it as `gpu_baseline` and `bench.py --impl torch_gpu` prints it alone.
 
-    python tools/torch_stock_baseline.py [--variant medium] [--batch 32] [--steps 3]
-
-Status: written after this round's GPU budget was spent -- smoke-tested on CPU only (`--cpu --variant tiny`); the B200
-number is the first measurement of the next round.
+    python -m baseline.torch_stock [--variant medium] [--batch 32] [--steps 3]
 """
 import argparse
 import math
@@ -18,6 +18,78 @@ import torch.nn.functional as F
 from torch import nn
 
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+
+
+def _f(x):
+    return float(x.detach()) if torch.is_tensor(x) else float(x)
+
+
+def run(variant: str, batch: int, steps: int, warmup: int, device, rank: int = 0, world: int = 1, e2e: bool = False):
+    """Timed stock-PyTorch training steps on `device` (DDP when world > 1).  Returns dict(ms_per_step, clips_per_s (this
+    rank's batch / step time x world), loss, peak_mem_gib).  Inputs are resident on the device unless e2e."""
+    import olmoasr_b200 as ob
+    from olmoasr_b200 import audio as A
+    from olmoasr_b200 import synthetic as synth
+
+    torch.manual_seed(0)
+    dims = ob.VARIANT_TO_DIMS[variant]
+    model = Model(dims).to(device)
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[device.index], output_device=device.index)
+    opt = torch.optim.AdamW(model.parameters(), lr=1.5e-3, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.1, fused=device.type == "cuda")
+    wav_h = synth.waveforms(batch, rank=rank, int16=True)
+    ti_h, ty_h, pm_h, _ = synth.text_batch(batch, rank=rank)
+    if device.type == "cuda":
+        wav_h, ti_h, ty_h, pm_h = (t.pin_memory() for t in (wav_h, ti_h, ty_h, pm_h))
+    dev_in = [t.to(device) for t in (wav_h, ti_h, ty_h, pm_h)]
+    filters = torch.as_tensor(A.mel_filterbank(80), dtype=torch.float32, device=device)
+
+    def step(wav, ti, ty, pm):
+        mel = log_mel_torch(wav.float() / 32768.0, filters)     # the reference runs this on CPU workers; here on the GPU
+        with torch.autocast(device.type, dtype=torch.bfloat16):
+            logits = net(mel, ti, pm)
+            loss = F.cross_entropy(logits.view(-1, logits.shape[-1]), ty.view(-1), ignore_index=51864)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        return loss
+
+    def one():
+        if e2e:
+            return step(*[t.to(device, non_blocking=True) for t in (wav_h, ti_h, ty_h, pm_h)]).item()
+        return step(*dev_in)
+
+    for _ in range(warmup):
+        loss = one()
+    if device.type != "cuda":
+        import time
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            loss = one()
+        ms = (time.perf_counter() - t0) * 1e3 / steps
+        return dict(ms_per_step=ms, clips_per_s=batch * world / ms * 1e3, loss=_f(loss), peak_mem_gib=0.0)
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = one()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    out = dict(ms_per_step=ms, clips_per_s=batch * world / ms * 1e3, loss=_f(loss), peak_mem_gib=torch.cuda.max_memory_allocated() / 2**30)
+    del net, model, opt
+    return out
 
 
 class LN(nn.LayerNorm):
@@ -112,51 +184,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--cpu", action="store_true")
     args = ap.parse_args()
-    import olmoasr_b200 as ob
-    from olmoasr_b200 import audio as A
-    from olmoasr_b200 import synthetic as synth
-
     dev = torch.device("cpu" if args.cpu else "cuda:0")
-    torch.manual_seed(0)
-    dims = ob.VARIANT_TO_DIMS[args.variant]
-    model = Model(dims).to(dev)
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.1, fused=not args.cpu)
-    B = args.batch
-    wav = (synth.waveforms(B, int16=True).float() / 32768.0).to(dev)
-    ti, ty, pm, _ = (t.to(dev) for t in synth.text_batch(B))
-    filters = torch.as_tensor(A.mel_filterbank(80), dtype=torch.float32, device=dev)
-
-    def step():
-        mel = log_mel_torch(wav, filters)
-        with torch.autocast(dev.type, dtype=torch.bfloat16):
-            logits = model(mel, ti, pm)
-            loss = F.cross_entropy(logits.view(-1, logits.shape[-1]), ty.view(-1), ignore_index=51864)
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
-        opt.step()
-        return loss
-
-    for _ in range(args.warmup):
-        loss = step()
-    if args.cpu:
-        import time
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            loss = step()
-        ms = (time.perf_counter() - t0) * 1e3 / args.steps
-    else:
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            loss = step()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / args.steps
-    mem = 0 if args.cpu else torch.cuda.max_memory_allocated() / 2**30
-    print(f"stock PyTorch ({torch.__version__}) {args.variant} B={B} bf16 autocast: {ms:.1f} ms/step = {B / ms * 1e3:.1f} clips/s, "
-          f"loss {float(loss):.4f}, peak memory {mem:.1f} GiB")
+    r = run(args.variant, args.batch, args.steps, args.warmup, dev)
+    print(f"stock PyTorch ({torch.__version__}) {args.variant} B={args.batch} bf16 autocast: {r['ms_per_step']:.1f} ms/step = "
+          f"{r['clips_per_s']:.1f} clips/s, loss {r['loss']:.4f}, peak memory {r['peak_mem_gib']:.1f} GiB")
 
 
 if __name__ == "__main__":

@@ -92,43 +92,33 @@ def run_cpu_reference(variant: str, clips: int, steps: int, warmup: int, layers=
     return clips * steps / dt, dt / steps, threads
 
 
-def bounded_cpu_sample(variant: str):
-    """~10-60 s of CPU work: one clip through the full-width model at depth 1+1 and 3+3; the per-layer-pair cost is
-    the difference and the full-depth step time is extrapolated linearly (stem, embedding, logits/CE and the
-    embedding's optimizer state are in the depth-1 term)."""
-    from oracle import model as OM
-
-    L = OM.variant_dims(variant).n_audio_layer
-    _, t1, threads = run_cpu_reference(variant, 1, 1, 1, layers=(1, 1))
-    _, t2, _ = run_cpu_reference(variant, 1, 1, 1, layers=(3, 3))
-    per_pair = max(t2 - t1, 0.0) / 2.0
-    full = t1 + (L - 1) * per_pair
-    return 1.0 / full, threads, (f"1 clip, {variant} width, fp32, torch CPU ({threads} threads): timed depth 1+1 ({t1:.2f} s) and "
-                                 f"3+3 ({t2:.2f} s) steps incl. log-mel/CE/bwd/clip/AdamW, extrapolated linearly to {L}+{L} layers "
-                                 f"({full:.1f} s per clip)")
+def bounded_cpu_sample(variant: str, steps: int = 2, warmup: int = 1):
+    """A bounded sample of the workload on the host cores: REAL full-depth optimizer steps of the reference's CPU path
+    on ONE clip (the GPU arm's step is 32 clips; ~4 s per clip-step at medium on the B200 box's host), nothing
+    extrapolated.  Returns (clips/s, threads, description, seconds per step, steps run)."""
+    value, sec, threads = run_cpu_reference(variant, 1, steps, warmup)
+    return value, threads, (f"{steps} full-depth optimizer steps of 1 clip each after {warmup} warm-up step(s): {variant}, fp32, torch CPU, "
+                            f"{threads} threads, log-mel + fwd + CE + bwd + clip + AdamW ({sec:.2f} s per step)"), sec, steps
 
 
 def reference_arm(args):
+    """`--impl reference`: the reference's own CPU implementation of the path (oracle port, bit-identical model code) on the
+    host cores.  Every step is a real full-depth step on a bounded sample (1 clip); at most 3 timed steps and 1 warm-up
+    are run whatever --steps / --warmup say, and the line reports the counts actually executed."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    clips = 1
-    # each "step" of this arm is the bounded sample (extrapolated full-depth step, see bounded_cpu_sample)
-    vals = []
-    sample = ""
-    for _ in range(max(1, min(args.steps, 3))):
-        v, threads, sample = bounded_cpu_sample(args.variant)
-        vals.append(v)
-    value = sum(vals) / len(vals)
-    sec_per_step = 1.0 / value
+    steps = max(1, min(args.steps, 3))
+    warmup = max(0, min(args.warmup, 1))
+    value, threads, sample, sec, _ = bounded_cpu_sample(args.variant, steps, warmup)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "steps_requested": args.steps, "warmup_requested": args.warmup,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.variant} training step, 30 s synthetic clips (reference CPU path, {clips} clip per step)",
-                   "global_batch": clips, "parallelism": "cpu"},
-        "cpu_baseline": {"value": value, "unit": "clips/s", "cores": threads, "kind": "port",
-                         "sample": sample},
+        "config": {"workload": f"{args.variant} training step, 30 s synthetic clips (reference CPU path, 1 clip per step)",
+                   "global_batch": 1, "parallelism": "cpu"},
+        "cpu_baseline": {"value": value, "unit": "clips/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -185,6 +175,66 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def _setup_dist():
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+    return world, rank, local_rank, dev
+
+
+def gpu_baseline_leg(args, world, rank, dev, steps=None):
+    """The reference's GPU path (stock PyTorch: cuBLASLt / cuDNN / ATen SDPA, autocast bf16, DDP, clip_grad_norm_, fused
+    torch AdamW) on the same synthetic batch, same box, same N -- the denominator north_star names.  Run after our own
+    arm has released its memory."""
+    import gc
+
+    from baseline import torch_stock
+
+    gc.collect()
+    torch.cuda.empty_cache()
+    torch.cuda.reset_peak_memory_stats()
+    steps = steps or max(2, min(args.steps, 5))
+    B = args.batch_per_gpu
+    note = ""
+    try:
+        r = torch_stock.run(args.variant, B, steps, 2, dev, rank=rank, world=world)
+    except torch.OutOfMemoryError:
+        gc.collect()
+        torch.cuda.empty_cache()
+        note = f"out of memory at {B} clips per GPU"
+        return {"value": None, "unit": "clips/s", "impl": "stock PyTorch", "unavailable": note}
+    return {"value": r["clips_per_s"], "unit": "clips/s", "ms_per_step": r["ms_per_step"], "steps": steps, "warmup": 2,
+            "impl": f"stock PyTorch {torch.__version__} (baseline/torch_stock.py): nn.Linear / Conv1d / fp32 F.layer_norm / "
+                    "F.scaled_dot_product_attention with the dense float mask / fp32 logits + F.cross_entropy, autocast bf16, "
+                    + ("DistributedDataParallel, " if world > 1 else "") + "clip_grad_norm_ + fused torch.optim.AdamW; log-mel by "
+                    "torch.stft on the GPU (the reference computes it in CPU workers, outside its step time)",
+            "clips_per_gpu": B, "loss": r["loss"], "peak_mem_gib": r["peak_mem_gib"]}
+
+
+def torch_gpu_arm(args):
+    """`--impl torch_gpu`: the stock-PyTorch GPU arm alone, same JSON shape."""
+    import torch.distributed as dist
+
+    world, rank, local_rank, dev = _setup_dist()
+    g = gpu_baseline_leg(args, world, rank, dev, steps=args.steps)
+    if rank == 0:
+        line = {"impl": "torch_gpu", "metric": METRIC, "value": g.get("value"), "unit": "clips/s", "n_gpus": world,
+                "steps": g.get("steps"), "warmup": g.get("warmup"), "ms_per_step": g.get("ms_per_step"), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"{args.variant} model DDP training bf16, {args.batch_per_gpu} x 30 s synthetic clips per GPU",
+                           "global_batch": args.batch_per_gpu * world, "parallelism": f"dp{world}"},
+                "gpu_baseline": g}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def our_arm(args):
     import torch.distributed as dist
 
@@ -195,13 +245,7 @@ def our_arm(args):
     from olmoasr_b200.optim import FusedAdamW
     from olmoasr_b200 import synthetic as synth
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    world, rank, local_rank, dev = _setup_dist()
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
 
     dims = ob.VARIANT_TO_DIMS[args.variant]
@@ -210,14 +254,17 @@ def our_arm(args):
     with torch.device(dev):
         model = OLMoASR(dims)
     net = model
-    reducer = None
-    ddp_impl = os.environ.get("OASR_DDP_IMPL", "torch")   # "blockwise": olmoasr_b200.ddp (opt-in until measured on NVLink)
-    if world > 1 and ddp_impl == "blockwise":
-        from olmoasr_b200.ddp import BlockwiseGradReducer
-        reducer = BlockwiseGradReducer(model)
+    sync = None
+    # gradient synchronisation: "slab" (default) = olmoasr_b200.ddp.SlabGradSync over the flat gradient slab;
+    # "torch" = torch DistributedDataParallel (the reference's wrapper) for A/B runs
+    ddp_impl = os.environ.get("OASR_DDP_IMPL", "slab")
+    slabs = model.use_slabs(direct_grads=(ddp_impl == "slab"))
+    if world > 1 and ddp_impl == "slab":
+        from olmoasr_b200.ddp import SlabGradSync
+        sync = SlabGradSync(model, slabs, bucket_bytes=int(os.environ.get("OASR_BUCKET_MB", "256")) << 20)
     elif world > 1:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], output_device=local_rank)
-    opt = FusedAdamW(model.parameters(), lr=1.5e-3, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.1, max_grad_norm=1.0)
+    opt = FusedAdamW(model.parameters(), lr=1.5e-3, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.1, max_grad_norm=1.0, slabs=slabs)
 
     # synthetic batch of SURVEY.md 8(d); host copies are pinned (what a DataLoader with pin_memory hands over)
     wav_h = synth.waveforms(B, rank=rank, int16=True).pin_memory()
@@ -229,13 +276,10 @@ def our_arm(args):
     def train_step(wav, ti, ty, pm):
         mel = ob.log_mel_spectrogram(wav)
         loss = net(mel, ti, pm, targets=ty)
-        opt.zero_grad(set_to_none=True)
+        opt.zero_grad()
         loss.backward()
-        if reducer is not None:
-            opt.step(inv_scale=reducer.finish())
-        else:
-            opt.step()
-        return loss
+        opt.step(inv_scale=sync.finish() if sync is not None else 1.0)
+        return loss.detach()
 
     def barrier():
         if world > 1:
@@ -263,7 +307,7 @@ def our_arm(args):
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, last
+        return ms, (last if e2e else float(last.item()))
 
     for _ in range(args.warmup):
         train_step(*dev_in)
@@ -287,6 +331,17 @@ def our_arm(args):
     _core.SIDE_STREAM = side_prev
     gemm_flops = sum(p[0] for p in prof)
     gemm_ms = sum(p[1].elapsed_time(p[2]) for p in prof)
+    n_gemm = len(prof)
+    applied = opt.applied_steps()
+    peak_mem = torch.cuda.max_memory_allocated() / 2**30
+
+    # release everything of ours before the stock-PyTorch leg
+    if sync is not None:
+        sync.remove()
+    del prof, net, model, opt, slabs, sync, dev_in
+    gpu_base = None
+    if not args.no_gpu_baseline:
+        gpu_base = gpu_baseline_leg(args, world, rank, dev)
 
     if rank != 0:
         if world > 1:
@@ -306,10 +361,11 @@ def our_arm(args):
                                f"(BASELINE.json configs[2] at {world} GPU(s)): int16 waveform -> log-mel -> fwd/bwd -> CE -> "
                                f"{'NCCL all-reduce -> ' if world > 1 else ''}clip + AdamW",
                    "global_batch": global_batch, "parallelism": f"dp{world}",
-                   "grad_sync": ("none" if world == 1 else ("olmoasr_b200.ddp.BlockwiseGradReducer" if reducer is not None
-                                                            else "torch DistributedDataParallel")),
+                   "grad_sync": ("none" if world == 1 else ("olmoasr_b200.ddp.SlabGradSync (flat fp32 gradient slab, segment all-reduces)"
+                                                            if ddp_impl == "slab" else "torch DistributedDataParallel")),
+                   "state_layout": "parameter / gradient / moment / bf16-shadow slabs (olmoasr_b200/slab.py); AdamW refreshes the bf16 weights",
                    "l2": "no flush needed: per-step working set (~60 GB of activations at medium/32) is >> the 126 MB L2",
-                   "loss": float(loss)},
+                   "loss": loss, "optimizer_steps_applied": applied, "peak_mem_gib": peak_mem},
         "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps, "loss": loss_e2e},
         "gpu_launches": launches,
@@ -321,11 +377,15 @@ def our_arm(args):
                      "measured_in": "a second pass of the same K steps with the weight-gradient side stream off (launches "
                                     "serialised, so each launch's CUDA-event time is its own duration)",
                      "serial_ms_per_step": ms_serial / args.steps,
-                     "gemm_share_of_step": gemm_ms / ms_serial, "gemm_launches": len(prof),
+                     "gemm_share_of_step": gemm_ms / ms_serial, "gemm_launches": n_gemm,
                      "whole_step_tflops_per_gpu": step_tflops, "whole_step_frac": step_tflops / peaks["bf16_tflops_sustained"]},
     }
+    if gpu_base is not None:
+        line["gpu_baseline"] = gpu_base
+        if gpu_base.get("value"):
+            line["gpu_baseline"]["ours_over_stock"] = value / gpu_base["value"]
     if world == 1 and not args.no_cpu_baseline:
-        v, threads, sample = bounded_cpu_sample(args.variant)
+        v, threads, sample, _, _ = bounded_cpu_sample(args.variant)
         line["cpu_baseline"] = {"value": v, "unit": "clips/s", "cores": threads, "kind": "port", "sample": sample}
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -337,13 +397,16 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_gpu"])
     ap.add_argument("--variant", default="medium", choices=list(TRAIN_GFLOP_PER_CLIP))
     ap.add_argument("--batch-per-gpu", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
+    elif args.impl == "torch_gpu":
+        torch_gpu_arm(args)
     else:
         our_arm(args)
 

@@ -110,10 +110,12 @@ OASR_API int oasr_attention_bwd(const void* q, int64_t ldq, const void* k, int64
 /* ---- token cross-entropy over bf16 logits ---------------------------------------------------------
  * Replaces F.cross_entropy(logits.view(-1,V), y.view(-1), ignore_index) (train_timestamps.py:1444-1448).
  * logits: (rows, ld) bf16, first V columns valid.  Forward writes lse (rows,) f32 (natural log) and ADDS
- * [sum of row losses, number of non-ignored rows] into loss_sum_count[2] (zero it first).  Backward
+ * [sum of row losses, number of non-ignored rows, number of targets outside [0, V) that are not ignore_index] into
+ * loss_sum_count[0..2] (4 floats, zero them first); ce_finalize writes the mean loss to loss[0].  Backward
  * overwrites logits in place with bf16(grad_out / count * (softmax - onehot)); ignored rows become zero. */
 OASR_API int oasr_ce_fwd(const void* logits, const int64_t* targets, float* lse, float* loss_sum_count,
                          int64_t rows, int64_t V, int64_t ld, int64_t ignore_index, void* stream);
+OASR_API int oasr_ce_finalize(const float* loss_sum_count, float* loss, void* stream);
 OASR_API int oasr_ce_bwd(void* logits, const int64_t* targets, const float* lse, const float* loss_sum_count,
                          const float* grad_out, int64_t rows, int64_t V, int64_t ld, int64_t ignore_index,
                          void* stream);
@@ -135,10 +137,14 @@ OASR_API int oasr_embed_bwd(const int64_t* ids, const void* dx, float* demb, flo
  * im2col_conv2: h (B, T_in, d) bf16 -> (B*T_out, 3d) bf16, rows 2t-1, 2t, 2t+1 (stride 2, pad 1) (model.py:593)
  * col2im_conv2_gelu_bwd: gradient w.r.t. conv2's input gathered back and multiplied by gelu'(pre1)
  * add_pos: (x + positional_embedding).to(x.dtype)                                              (model.py:602)
- * gelu_bwd: dy * gelu_erf'(pre);  colsum_bf16: db[n] += sum_m dy[m,n] (bias gradients, ACCUMULATES). */
+ * gelu_bwd: dy * gelu_erf'(pre);  colsum_bf16: db[n] += sum_m dy[m,n] (bias gradients, ACCUMULATES).
+ * unpermute_conv_wgrad: accumulate != 0 adds into dst (a gradient-slab view) instead of overwriting it.
+ * mask_to_kvlen: the decoder's dense additive padding mask (B, S, S) f32 (train_timestamps.py:314-315, model.py:740-743)
+ *   -> kv_len[b] = number of un-masked key columns; err[0] |= 1 when some row is not [0]*len + [-inf]*(S-len). */
 OASR_API int oasr_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 OASR_API int oasr_cast_conv_weight(const float* src, void* dst, int64_t c_out, int64_t c_in, void* stream);
-OASR_API int oasr_unpermute_conv_wgrad(const float* src, float* dst, int64_t c_out, int64_t c_in, void* stream);
+OASR_API int oasr_unpermute_conv_wgrad(const float* src, float* dst, int64_t c_out, int64_t c_in, int accumulate,
+                                       void* stream);
 OASR_API int oasr_im2col_conv1(const float* mel, void* A, int64_t batch, int64_t C, int64_t T, int64_t kpad, void* stream);
 OASR_API int oasr_im2col_conv2(const void* h, void* A, int64_t batch, int64_t T_in, int64_t T_out, int64_t d, void* stream);
 OASR_API int oasr_col2im_conv2_gelu_bwd(const void* dA, const void* pre1, void* dpre1, int64_t batch, int64_t T_in,
@@ -146,17 +152,30 @@ OASR_API int oasr_col2im_conv2_gelu_bwd(const void* dA, const void* pre1, void* 
 OASR_API int oasr_add_pos(const void* x, const float* pos, void* out, int64_t rows, int64_t T, int64_t d, void* stream);
 OASR_API int oasr_gelu_bwd(const void* dy, const void* pre, void* out, int64_t n, void* stream);
 OASR_API int oasr_colsum_bf16(const void* dy, float* db, int64_t M, int64_t N, int64_t ld, void* stream);
+OASR_API int oasr_mask_to_kvlen(const float* mask, int32_t* kv_len, int32_t* err, int64_t batch, int64_t S, void* stream);
 
 /* ---- fused optimizer step ("next" row: scripts/training/train_timestamps.py:1508-1522) -----------------
- * recs: device table of {float* p, const float* g, float* m, float* v, int64 numel} per tensor; chunks: device
- * int2 {tensor index, chunk index} with oasr_optim_chunk_elems() elements per chunk.  grad_sqnorm writes the sum
- * of squares of all gradients to out[0]; adamw_step applies unscale (inv_scale), clip_grad_norm_(max_norm) and the
- * AdamW update, and leaves everything untouched (found_inf[0] = 1) when the norm is not finite. */
+ * Replaces scaler.unscale_ -> clip_grad_norm_(max_norm) -> scaler.step(AdamW) (:1509-1521; AdamW defaults :2110-2113).
+ * Three launches for the whole model: (1) sum of squares of the UNSCALED gradients (inv_scale is applied before
+ * squaring) into out[0]; (2) optim_prepare, one thread: state[0] step (advanced only when the norm is finite: skipped
+ * steps are not counted, like GradScaler + AdamW), state[1] unscale x clip coefficient, state[2] 1 - beta1^t,
+ * state[3] sqrt(1 - beta2^t), state[4] skip flag, state[5] gradient norm; found_inf[0] = 1 on a non-finite norm;
+ * (3) the AdamW update, which also refreshes an optional bf16 shadow of every parameter (the per-forward
+ * `weight.to(x.dtype)` of model.py:97-101 never runs).  `state` is 8 floats on the device, zero-initialised.
+ * Table form: recs = device table of {float* p, const float* g, float* m, float* v, int64 numel, bf16* shadow|NULL}
+ * per tensor; chunks = device int2 {tensor index, chunk index}, oasr_optim_chunk_elems() elements per chunk.
+ * Flat form: parameters, gradients, moments and shadow each live in ONE contiguous slab (olmoasr_b200/slab.py). */
 OASR_API int oasr_optim_chunk_elems(void);
-OASR_API int oasr_grad_sqnorm(const void* recs, const void* chunks, int64_t n_chunks, float* out, void* stream);
-OASR_API int oasr_adamw_step(const void* recs, const void* chunks, int64_t n_chunks, const float* norm_sq,
-                             float* found_inf, float inv_scale, float max_norm, float lr, float beta1, float beta2,
-                             float eps, float weight_decay, int64_t step, void* stream);
+OASR_API int oasr_grad_sqnorm(const void* recs, const void* chunks, int64_t n_chunks, float inv_scale, float* out,
+                              void* stream);
+OASR_API int oasr_grad_sqnorm_flat(const float* g, int64_t numel, float inv_scale, float* out, void* stream);
+OASR_API int oasr_optim_prepare(const float* norm_sq, float* found_inf, float* state, float inv_scale, float max_norm,
+                                float beta1, float beta2, void* stream);
+OASR_API int oasr_adamw_step(const void* recs, const void* chunks, int64_t n_chunks, const float* state, float lr,
+                             float beta1, float beta2, float eps, float weight_decay, void* stream);
+OASR_API int oasr_adamw_flat(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t numel,
+                             const float* state, float lr, float beta1, float beta2, float eps, float weight_decay,
+                             void* stream);
 
 #ifdef __cplusplus
 }

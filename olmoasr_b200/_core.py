@@ -78,10 +78,11 @@ def linear_dgrad(dy: Tensor, w_bf16: Tensor, *, epi=K.EPI_BF16, aux=None, out=No
     return K.gemm(dy, w_bf16, M, Kd, N, b_mn=True, epi=epi, aux=aux, out=out, block_n=_pick_block_n(M, Kd))
 
 
-def linear_wgrad(dy: Tensor, x: Tensor, n_valid: Optional[int] = None, side=None):
+def linear_wgrad(dy: Tensor, x: Tensor, n_valid: Optional[int] = None, side=None, out: Optional[Tensor] = None):
     """dW (N, K) f32 = dy^T x.  Both operands are read MN-major straight from their (M, *) row-major storage
     (A = dy^T is "stored (K=M, M=N)", B = x is "stored (K=M, N=K)"); split-K + fp32 red.add when the output has
-    too few tiles to fill the GPU."""
+    too few tiles to fill the GPU.  With `out` (a gradient-slab view, olmoasr_b200/slab.py) the product is ACCUMULATED
+    into it by the epilogue: no allocation, no zero fill, no hand-over through autograd."""
     M = dy.shape[0]
     N = dy.shape[1] if n_valid is None else n_valid
     Kd = x.shape[1]
@@ -89,12 +90,14 @@ def linear_wgrad(dy: Tensor, x: Tensor, n_valid: Optional[int] = None, side=None
     tiles = math.ceil(N / 128) * math.ceil(Kd / bn)
     split = _pick_split_k(tiles, math.ceil(M / 64))
     dyv = dy if n_valid is None else dy[:, :n_valid]
-    alloc = torch.empty if split == 1 else torch.zeros     # allocated (and zeroed) on the caller's stream
-    out = alloc((N, Kd), device=x.device, dtype=torch.float32)
+    accumulate = out is not None
+    if out is None:
+        alloc = torch.empty if split == 1 else torch.zeros     # allocated (and zeroed) on the caller's stream
+        out = alloc((N, Kd), device=x.device, dtype=torch.float32)
 
     def launch():
         return K.gemm(dyv, x, N, Kd, M, a_mn=True, b_mn=True, out=out,
-                      epi=K.EPI_F32 if split == 1 else K.EPI_F32_ATOMIC_ADD, split_k=split, block_n=bn)
+                      epi=K.EPI_F32 if (split == 1 and not accumulate) else K.EPI_F32_ATOMIC_ADD, split_k=split, block_n=bn)
 
     return side.run(launch) if side is not None else launch()
 
@@ -116,9 +119,10 @@ class _ZeroPool:
         return v
 
 
-def bias_grad(dy: Tensor, n: Optional[int] = None, pool: Optional[_ZeroPool] = None, side=None) -> Tensor:
+def bias_grad(dy: Tensor, n: Optional[int] = None, pool: Optional[_ZeroPool] = None, side=None, out: Optional[Tensor] = None) -> Tensor:
+    """Column sums of dy (M, >= n) bf16, accumulated into `out` (a gradient-slab view) or a fresh zeroed vector."""
     n = dy.shape[1] if n is None else n
-    db = pool.take(n) if pool is not None else torch.zeros(n, device=dy.device, dtype=torch.float32)
+    db = out if out is not None else (pool.take(n) if pool is not None else torch.zeros(n, device=dy.device, dtype=torch.float32))
     if side is not None:
         return side.run(lambda: K.colsum_(dy, db, n))
     return K.colsum_(dy, db, n)
@@ -160,13 +164,54 @@ class _Side:
             self.main.wait_stream(self.side)
 
 
+STRICT_MASK = os.environ.get("OASR_STRICT_MASK", "0") == "1"
+_mask_err: Dict[int, tuple] = {}   # device index -> (device flag, pinned host flag, event of the last flag copy)
+
+
+def check_deferred_errors(device=None, wait: bool = False):
+    """Raise if an earlier padding_mask failed validation.  The check itself never stalls the stream: the kernel that
+    derives the key counts also verifies the mask and raises a flag that is copied to pinned memory asynchronously; it is
+    looked at on the NEXT call (or here, with wait=True / OASR_STRICT_MASK=1: immediately, at the cost of a sync)."""
+    idx = torch.cuda.current_device() if device is None else (device.index if device.index is not None else torch.cuda.current_device())
+    st = _mask_err.get(idx)
+    if st is None or st[2] is None:
+        return
+    flag, host, ev = st
+    if wait:
+        ev.synchronize()
+    if ev.query() and int(host[0]) != 0:
+        host[0] = 0
+        flag.zero_()
+        raise ValueError("padding_mask is not of the form [0]*len + [-inf]*(n_ctx-len) on every row (the only structure "
+                         "scripts/training/train_timestamps.py:314-315 produces); this implementation derives a per-sample "
+                         "key count from it and supports no other additive mask")
+
+
 def kv_len_from_padding_mask(padding_mask: Tensor) -> Tensor:
     """The reference passes a dense additive mask (B, 448, 448) whose columns >= len(text_input) are -inf for every
-    row (scripts/training/train_timestamps.py:314-315).  The kernels take that as a per-sample key count."""
+    row (scripts/training/train_timestamps.py:314-315).  The kernels take that as a per-sample key count, derived -- and
+    the structure verified -- on the device.  A 1-D integer tensor is taken as the key counts themselves (what a data
+    loader that never builds the 25.7 MB mask would pass)."""
+    if padding_mask.dim() == 1 and not padding_mask.is_floating_point():
+        return padding_mask if padding_mask.dtype == torch.int32 else padding_mask.to(torch.int32)
     cached = getattr(padding_mask, "_oasr_kv_len", None)   # computed once per decoder call, not once per block
     if cached is not None and cached[0] == padding_mask._version:
         return cached[1]
-    kv = (padding_mask[:, 0, :] == 0).sum(dim=-1).to(torch.int32)
+    if padding_mask.dim() != 3 or padding_mask.shape[1] != padding_mask.shape[2] or padding_mask.dtype != torch.float32:
+        raise ValueError(f"padding_mask must be (B, n_ctx, n_ctx) float32, got {tuple(padding_mask.shape)} {padding_mask.dtype}")
+    dev = padding_mask.device
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    check_deferred_errors(dev)
+    if idx not in _mask_err:
+        _mask_err[idx] = (torch.zeros(1, device=dev, dtype=torch.int32), torch.zeros(1, dtype=torch.int32).pin_memory(), None)
+    flag, host, _ = _mask_err[idx]
+    kv = K.mask_to_kvlen(padding_mask.contiguous(), flag)
+    host.copy_(flag, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    _mask_err[idx] = (flag, host, ev)
+    if STRICT_MASK:
+        check_deferred_errors(dev, wait=True)
     try:
         padding_mask._oasr_kv_len = (padding_mask._version, kv)   # rides on this tensor object; in-place edits invalidate
     except (AttributeError, RuntimeError):
@@ -210,7 +255,11 @@ class Linear(nn.Linear):
         nn.init.kaiming_normal_(self.weight, mode="fan_in", nonlinearity="relu")
         self._shadow = _ShadowCache()
 
+    _slab_view: Optional[Tensor] = None   # set by OLMoASRBase.use_slabs(): a view into the bf16 shadow slab
+
     def weight_bf16(self) -> Tensor:
+        if self._slab_view is not None:
+            return self._slab_view
         return self._shadow.get((self.weight,), lambda: K.cast_bf16(self.weight.detach().contiguous()))
 
     def forward(self, x: Tensor) -> Tensor:  # inference / hook path (no autograd through the kernels)
@@ -270,8 +319,12 @@ class MultiHeadAttention(nn.Module):
         self._fused = _ShadowCache()
 
     # ---- fused bf16 shadows -------------------------------------------------------------------------
+    _slab_fused = None   # set by OLMoASRBase.use_slabs(): ([Wq;Wk;Wv] view of the shadow slab, [bq;0;bv] view of the masters)
+
     def fused_qkv(self):
         """([Wq;Wk;Wv] (3d, d) bf16, [bq;0;bv] (3d,) f32) -- key has no bias (model.py:259)."""
+        if self._slab_fused is not None:
+            return self._slab_fused
         ps = (self.query.weight, self.key.weight, self.value.weight, self.query.bias, self.value.bias)
 
         def build():
@@ -368,59 +421,82 @@ class _BlockFn(torch.autograd.Function):
             mean2, rstd2, ln2, h, g = sv[8:13]
         dx3 = dx3.contiguous()
         dev = x.device
+        # Where the parameter gradients go.  Slab mode (OLMoASRBase.use_slabs + direct_grads): every kernel ACCUMULATES into
+        # its parameter's slice of the flat gradient slab and autograd is handed None.  Otherwise: fresh tensors returned
+        # to autograd (DistributedDataParallel / any foreign optimizer keep working).
+        D = blk._direct if (blk._direct is not None and blk._slabs.direct_grads) else None
         grads: Dict[str, Tensor] = {}
-        pool = _ZeroPool(32 * d + 4096, dev)   # all bias / LayerNorm gradient vectors of this block (<= 26 d)
-        z = pool.take
+        pool = None if D is not None else _ZeroPool(32 * d + 4096, dev)   # all bias / LayerNorm gradient vectors (<= 26 d)
+        side = _Side(dev)
+
+        def wg(key, dy, xin):
+            return linear_wgrad(dy, xin, side=side, out=None if D is None else D[key])
+
+        def bg(key, dy, n=None):
+            return bias_grad(dy, n, pool=pool, side=side, out=None if D is None else D[key])
+
+        def vec(key):
+            return D[key] if D is not None else pool.take(d)
 
         # ---- MLP: x3 = x2 + fc2(gelu(fc1(ln(x2))))
-        side = _Side(dev)
-        grads["mlp.2.weight"] = linear_wgrad(dx3, g, side=side)
-        grads["mlp.2.bias"] = bias_grad(dx3, pool=pool, side=side)
+        grads["mlp.2.weight"] = wg("mlp.2.weight", dx3, g)
+        grads["mlp.2.bias"] = bg("mlp.2.bias", dx3)
         dh = linear_dgrad(dx3, sh["w2"], epi=K.EPI_BF16_GELU_BWD, aux=h)
-        grads["mlp.0.weight"] = linear_wgrad(dh, ln2, side=side)
-        grads["mlp.0.bias"] = bias_grad(dh, pool=pool, side=side)
+        grads["mlp.0.weight"] = wg("mlp.0.weight", dh, ln2)
+        grads["mlp.0.bias"] = bg("mlp.0.bias", dh)
         dln2 = linear_dgrad(dh, sh["w1"])
-        grads["mlp_ln.weight"], grads["mlp_ln.bias"] = z(d), z(d)
+        grads["mlp_ln.weight"], grads["mlp_ln.bias"] = vec("mlp_ln.weight"), vec("mlp_ln.bias")
         dx2 = K.layernorm_bwd(dln2, x2, blk.mlp_ln.weight, mean2, rstd2, grads["mlp_ln.weight"], grads["mlp_ln.bias"],
                               dresidual=dx3)
         dxa = None
         if cross:
             # ---- cross attention: x2 = x1 + out(attn(q(ln(x1)), kv(xa)))
-            grads["cross_attn.out.weight"] = linear_wgrad(dx2, co, side=side)
-            grads["cross_attn.out.bias"] = bias_grad(dx2, pool=pool, side=side)
+            grads["cross_attn.out.weight"] = wg("cross_attn.out.weight", dx2, co)
+            grads["cross_attn.out.bias"] = bg("cross_attn.out.bias", dx2)
             dco = linear_dgrad(dx2, sh["wco"])
             dqc = torch.empty_like(qc)
             dkvc = torch.empty_like(kvc)
             K.attention_bwd(qc, kvc[:, :d], kvc[:, d:], co, dco, lsec, B, H, T, Ta, dq=dqc, dk=dkvc[:, :d], dv=dkvc[:, d:])
-            grads["cross_attn.query.weight"] = linear_wgrad(dqc, lnc, side=side)
-            grads["cross_attn.query.bias"] = bias_grad(dqc, pool=pool, side=side)
-            dwkv = linear_wgrad(dkvc, xa, side=side)
-            grads["cross_attn.key.weight"], grads["cross_attn.value.weight"] = dwkv[:d], dwkv[d:]
-            grads["cross_attn.value.bias"] = bias_grad(dkvc, pool=pool, side=side)[d:]
+            grads["cross_attn.query.weight"] = wg("cross_attn.query.weight", dqc, lnc)
+            grads["cross_attn.query.bias"] = bg("cross_attn.query.bias", dqc)
+            dwkv = wg("cross_attn.kv.weight", dkvc, xa)     # [dWk; dWv] in one GEMM
+            if D is None:
+                grads["cross_attn.key.weight"], grads["cross_attn.value.weight"] = dwkv[:d], dwkv[d:]
+                grads["cross_attn.value.bias"] = bias_grad(dkvc, pool=pool, side=side)[d:]
+            else:
+                bias_grad(dkvc[:, d:], d, side=side, out=D["cross_attn.value.bias"])
             dxa = torch.empty_like(xa)   # only the encoder's backward reads it
             side.run(lambda: linear_dgrad(dkvc, sh["wckv"], out=dxa))
             dlnc = linear_dgrad(dqc, sh["wcq"])
-            grads["cross_attn_ln.weight"], grads["cross_attn_ln.bias"] = z(d), z(d)
+            grads["cross_attn_ln.weight"], grads["cross_attn_ln.bias"] = vec("cross_attn_ln.weight"), vec("cross_attn_ln.bias")
             dx1 = K.layernorm_bwd(dlnc, x1, blk.cross_attn_ln.weight, meanc, rstdc, grads["cross_attn_ln.weight"],
                                   grads["cross_attn_ln.bias"], dresidual=dx2)
         else:
             dx1 = dx2
         # ---- self attention: x1 = x + out(attn(qkv(ln(x))))
-        grads["attn.out.weight"] = linear_wgrad(dx1, ao, side=side)
-        grads["attn.out.bias"] = bias_grad(dx1, pool=pool, side=side)
+        grads["attn.out.weight"] = wg("attn.out.weight", dx1, ao)
+        grads["attn.out.bias"] = bg("attn.out.bias", dx1)
         dao = linear_dgrad(dx1, sh["wo"])
         dqkv = torch.empty_like(qkv)
         K.attention_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], ao, dao, lse, B, H, T, T, causal=causal, kv_len=kv_len,
                         dq=dqkv[:, :d], dk=dqkv[:, d:2 * d], dv=dqkv[:, 2 * d:])
-        dw = linear_wgrad(dqkv, ln1, side=side)
-        grads["attn.query.weight"], grads["attn.key.weight"], grads["attn.value.weight"] = dw[:d], dw[d:2 * d], dw[2 * d:]
-        db = bias_grad(dqkv, pool=pool, side=side)
-        grads["attn.query.bias"], grads["attn.value.bias"] = db[:d], db[2 * d:]
+        dw = wg("attn.qkv.weight", dqkv, ln1)               # [dWq; dWk; dWv] in one GEMM
+        if D is None:
+            grads["attn.query.weight"], grads["attn.key.weight"], grads["attn.value.weight"] = dw[:d], dw[d:2 * d], dw[2 * d:]
+            db = bias_grad(dqkv, pool=pool, side=side)
+            grads["attn.query.bias"], grads["attn.value.bias"] = db[:d], db[2 * d:]
+        else:   # the key projection has no bias (model.py:259): its slot in the fused [bq; 0; bv] vector must stay zero
+            bias_grad(dqkv[:, :d], d, side=side, out=D["attn.query.bias"])
+            bias_grad(dqkv[:, 2 * d:], d, side=side, out=D["attn.value.bias"])
         dln1 = linear_dgrad(dqkv, sh["wqkv"])
-        grads["attn_ln.weight"], grads["attn_ln.bias"] = z(d), z(d)
+        grads["attn_ln.weight"], grads["attn_ln.bias"] = vec("attn_ln.weight"), vec("attn_ln.bias")
         dx = K.layernorm_bwd(dln1, x, blk.attn_ln.weight, mean1, rstd1, grads["attn_ln.weight"], grads["attn_ln.bias"],
                              dresidual=dx1)
         side.join()
+        if D is not None:
+            if blk._bwd_done_cb is not None:
+                blk._bwd_done_cb()      # gradient synchronisation hook: this block's slab range is final
+            return (None, None, None, None, None, None, dx, dxa, *([None] * len(blk._param_names)))
         return (None, None, None, None, None, None, dx, dxa, *[grads[n] for n in blk._param_names])
 
 
@@ -438,8 +514,15 @@ class ResidualAttentionBlock(nn.Module):
         self.mlp_ln = LayerNorm(n_state)
         self._param_names = [n for n, _ in self.named_parameters()]
         self._shadow = _ShadowCache()
+        # slab mode (OLMoASRBase.use_slabs): precomputed operand views, gradient-slab targets, completion callback
+        self._slabs = None
+        self._slab_sh: Optional[Dict[str, Tensor]] = None
+        self._direct: Optional[Dict[str, Tensor]] = None
+        self._bwd_done_cb = None
 
     def _shadows(self):
+        if self._slab_sh is not None:
+            return self._slab_sh
         params = [p for _, p in self.named_parameters()]
 
         def build():
@@ -509,13 +592,18 @@ class _StemFn(torch.autograd.Function):
         A1, pre1, A2, pre2 = ctx.saved_tensors
         enc = ctx.enc
         B, C, T, T2, d = ctx.dims
+        D = enc._direct if (enc._direct is not None and enc._slabs.direct_grads) else None
         dpre2 = K.gelu_bwd(dx0.contiguous(), pre2)
-        dw2 = K.unpermute_conv_wgrad(linear_wgrad(dpre2, A2), d, d)
-        db2 = bias_grad(dpre2)
+        dw2 = K.unpermute_conv_wgrad(linear_wgrad(dpre2, A2), d, d, out=None if D is None else D["conv2.weight"])
+        db2 = bias_grad(dpre2, out=None if D is None else D["conv2.bias"])
         dA2 = linear_dgrad(dpre2, enc.conv2.weight_bf16())
         dpre1 = K.col2im_conv2_gelu_bwd(dA2, pre1, B, T, T2, d)
-        dw1 = K.unpermute_conv_wgrad(linear_wgrad(dpre1, A1), d, C)
-        db1 = bias_grad(dpre1)
+        dw1 = K.unpermute_conv_wgrad(linear_wgrad(dpre1, A1), d, C, out=None if D is None else D["conv1.weight"])
+        db1 = bias_grad(dpre1, out=None if D is None else D["conv1.bias"])
+        if D is not None:
+            if enc._bwd_done_cb is not None:
+                enc._bwd_done_cb()     # last gradients of the whole backward pass
+            return None, None, None, None, None, None
         return None, None, dw1, db1, dw2, db2
 
 
@@ -530,8 +618,13 @@ class AudioEncoder(nn.Module):
         self.blocks: Iterable[ResidualAttentionBlock] = nn.ModuleList(
             [ResidualAttentionBlock(n_state, n_head, double_init=double_init) for _ in range(n_layer)])
         self.ln_post = LayerNorm(n_state)
+        self._slabs = None
+        self._direct: Optional[Dict[str, Tensor]] = None
+        self._bwd_done_cb = None
 
     def forward(self, x: Tensor, verbose: bool = False):
+        if self._slabs is not None:
+            self._slabs.ensure_synced()
         B = x.shape[0]
         n_ctx, d = self.positional_embedding.shape
         assert x.dim() == 3 and (x.shape[2] + 2 - 3) // 2 + 1 == n_ctx and x.shape[1] == self.conv1.in_channels, \
@@ -540,23 +633,33 @@ class AudioEncoder(nn.Module):
         h = x0.view(B, n_ctx, d)
         for block in self.blocks:
             h = block(h)
-        return _LayerNormFn.apply(h.reshape(B * n_ctx, d), self.ln_post.weight, self.ln_post.bias, self.ln_post.eps).view(B, n_ctx, d)
+        return _LayerNormFn.apply(h.reshape(B * n_ctx, d), self.ln_post.weight, self.ln_post.bias, self.ln_post.eps,
+                                  self, "ln_post").view(B, n_ctx, d)
 
 
 class _LayerNormFn(torch.autograd.Function):
+    """Final LayerNorm of the encoder / decoder.  `owner._direct[key + ".weight" / ".bias"]` are the gradient-slab targets
+    in slab mode."""
+
     @staticmethod
-    def forward(ctx, x, w, b, eps):
+    def forward(ctx, x, w, b, eps, owner=None, key=None):
         y, mean, rstd = K.layernorm_fwd(x, w, b, eps)
         ctx.save_for_backward(x, w, mean, rstd)
+        ctx.owner, ctx.key = owner, key
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, w, mean, rstd = ctx.saved_tensors
+        owner = ctx.owner
+        D = owner._direct if (owner is not None and owner._direct is not None and owner._slabs.direct_grads) else None
+        if D is not None:
+            dx = K.layernorm_bwd(dy.contiguous(), x, w, mean, rstd, D[ctx.key + ".weight"], D[ctx.key + ".bias"])
+            return dx, None, None, None, None, None
         dw = torch.zeros_like(w)
         db = torch.zeros_like(w)
         dx = K.layernorm_bwd(dy.contiguous(), x, w, mean, rstd, dw, db)
-        return dx, dw, db, None
+        return dx, dw, db, None, None, None
 
 
 # =====================================================================================================
@@ -566,20 +669,36 @@ class _EmbedFn(torch.autograd.Function):
     """(token_embedding(ids) + positional_embedding[offset:offset+S]).to(bf16)  (model.py:728-732)."""
 
     @staticmethod
-    def forward(ctx, ids, emb, pos, offset, padding_idx):
+    def forward(ctx, ids, emb, pos, offset, padding_idx, dec=None):
         out = K.embed_fwd(ids.contiguous(), emb, pos, offset)
         ctx.save_for_backward(ids)
         ctx.meta = (emb.shape, pos.shape, offset, padding_idx)
+        ctx.dec = dec
         return out
 
     @staticmethod
     def backward(ctx, dx):
         (ids,) = ctx.saved_tensors
         eshape, pshape, offset, padding_idx = ctx.meta
+        dec = ctx.dec
+        pad = -1 if padding_idx is None else padding_idx
+        D = dec._direct if (dec is not None and dec._direct is not None and dec._slabs.direct_grads) else None
+        if D is not None:   # scatter-add straight into the slab (the tied logits wgrad already accumulated there)
+            K.embed_bwd(ids.contiguous(), dx.contiguous(), D["token_embedding.weight"], D["positional_embedding"][offset:], pad)
+            if dec._bwd_done_cb is not None:
+                dec._bwd_done_cb()     # decoder gradients (incl. the tied embedding) are final
+            return None, None, None, None, None, None
         demb = torch.zeros(eshape, device=dx.device, dtype=torch.float32)
         dpos = torch.zeros(pshape, device=dx.device, dtype=torch.float32)
-        K.embed_bwd(ids.contiguous(), dx.contiguous(), demb, dpos[offset:], -1 if padding_idx is None else padding_idx)
-        return None, demb, dpos, None, None
+        K.embed_bwd(ids.contiguous(), dx.contiguous(), demb, dpos[offset:], pad)
+        return None, demb, dpos, None, None, None
+
+
+def _direct_of(mod):
+    """Gradient-slab targets of a module when the model runs in slab mode with direct gradients, else None."""
+    if mod is not None and mod._direct is not None and mod._slabs.direct_grads:
+        return mod._direct
+    return None
 
 
 def _logits_ld(V: int) -> int:
@@ -590,12 +709,13 @@ class _LogitsFn(torch.autograd.Function):
     """(x @ token_embedding.weight.to(x.dtype).T).float()  (model.py:768-770) for callers that want logits."""
 
     @staticmethod
-    def forward(ctx, x, emb, emb_bf16):
+    def forward(ctx, x, emb, emb_bf16, dec=None):
         M, d = x.shape
         V = emb.shape[0]
         buf = torch.empty((M, _logits_ld(V)), device=x.device, dtype=torch.bfloat16)
         K.gemm(x, emb_bf16, M, V, d, out=buf, block_n=256)
         ctx.save_for_backward(x, emb_bf16)
+        ctx.dec = dec
         return K.logits_to_f32(buf, V)
 
     @staticmethod
@@ -606,8 +726,9 @@ class _LogitsFn(torch.autograd.Function):
         buf = torch.empty((M, _logits_ld(V)), device=x.device, dtype=torch.bfloat16)
         buf[:, :V].copy_(dlogits)  # `.float()` backward: the gradient enters the matmul as bf16
         dx = K.gemm(buf[:, :V], emb_bf16, M, d, V, b_mn=True, block_n=_pick_block_n(M, d))
-        demb = linear_wgrad(buf, x, n_valid=V)
-        return dx, demb, None
+        D = _direct_of(ctx.dec)
+        demb = linear_wgrad(buf, x, n_valid=V, out=None if D is None else D["token_embedding.weight"])
+        return dx, (None if D is not None else demb), None, None
 
 
 class _LossHeadFn(torch.autograd.Function):
@@ -616,7 +737,8 @@ class _LossHeadFn(torch.autograd.Function):
     d(logits) in place and feeds it to the dgrad / wgrad GEMMs."""
 
     @staticmethod
-    def forward(ctx, x, emb, emb_bf16, targets, ignore_index):
+    def forward(ctx, x, emb, emb_bf16, targets, ignore_index, dec=None):
+        ctx.dec = dec
         M, d = x.shape
         V = emb.shape[0]
         buf = torch.empty((M, _logits_ld(V)), device=x.device, dtype=torch.bfloat16)
@@ -625,17 +747,23 @@ class _LossHeadFn(torch.autograd.Function):
         lse, lsc = K.ce_fwd(buf, t, V, ignore_index)
         ctx.save_for_backward(x, emb_bf16, buf, t, lse, lsc)
         ctx.meta = (V, ignore_index)
-        return lsc[0] / lsc[1]
+        ctx.consumed = [False]
+        return K.ce_finalize(lsc)
 
     @staticmethod
     def backward(ctx, dloss):
         x, emb_bf16, buf, t, lse, lsc = ctx.saved_tensors
         V, ignore_index = ctx.meta
         M, d = x.shape
+        if ctx.consumed[0]:
+            raise RuntimeError("the fused loss head keeps d(logits) in the logits buffer: backward through it twice "
+                               "(retain_graph) is not supported")
+        ctx.consumed[0] = True
         K.ce_bwd_(buf, t, lse, lsc, dloss.reshape(1).float().contiguous(), V, ignore_index)
         dx = K.gemm(buf[:, :V], emb_bf16, M, d, V, b_mn=True, block_n=_pick_block_n(M, d))
-        demb = linear_wgrad(buf, x, n_valid=V)
-        return dx, demb, None, None, None
+        D = _direct_of(ctx.dec)
+        demb = linear_wgrad(buf, x, n_valid=V, out=None if D is None else D["token_embedding.weight"])
+        return dx, (None if D is not None else demb), None, None, None, None
 
 
 class TextDecoder(nn.Module):
@@ -658,33 +786,41 @@ class TextDecoder(nn.Module):
         mask = torch.empty(n_ctx, n_ctx).fill_(-np.inf).triu_(1)
         self.register_buffer("mask", mask, persistent=False)
         self._emb_shadow = _ShadowCache()
+        self._slabs = None
+        self._direct: Optional[Dict[str, Tensor]] = None
+        self._bwd_done_cb = None
+        self._emb_slab_view: Optional[Tensor] = None
 
     def embedding_bf16(self) -> Tensor:
+        if self._emb_slab_view is not None:
+            return self._emb_slab_view
         w = self.token_embedding.weight
         return self._emb_shadow.get((w,), lambda: K.cast_bf16(w.detach().contiguous()))
 
     def hidden(self, x: Tensor, xa: Tensor, kv_cache: Optional[dict] = None, padding_mask: Optional[Tensor] = None) -> Tensor:
         """Everything up to and including the final LayerNorm: (B, S) ids -> (B*S, d) bf16."""
+        if self._slabs is not None:
+            self._slabs.ensure_synced()
         offset = next(iter(kv_cache.values())).shape[1] if kv_cache else 0
         B, S = x.shape
         d = self.positional_embedding.shape[1]
         h = _EmbedFn.apply(x, self.token_embedding.weight, self.positional_embedding, offset,
-                           self.token_embedding.padding_idx).view(B, S, d)
+                           self.token_embedding.padding_idx, self).view(B, S, d)
         mask = padding_mask if padding_mask is not None else self.mask[:S, :S]
         for block in self.blocks:
             h = block(h, xa, mask=mask, kv_cache=kv_cache)
-        return _LayerNormFn.apply(h.reshape(B * S, d), self.ln.weight, self.ln.bias, self.ln.eps)
+        return _LayerNormFn.apply(h.reshape(B * S, d), self.ln.weight, self.ln.bias, self.ln.eps, self, "ln")
 
     def forward(self, x: Tensor, xa: Tensor, kv_cache: Optional[dict] = None, padding_mask: Optional[Tensor] = None,
                 verbose: bool = False):
         B, S = x.shape
         h = self.hidden(x, xa, kv_cache, padding_mask)
-        logits = _LogitsFn.apply(h, self.token_embedding.weight, self.embedding_bf16())
+        logits = _LogitsFn.apply(h, self.token_embedding.weight, self.embedding_bf16(), self)
         return logits.view(B, S, -1)
 
     def loss(self, x: Tensor, xa: Tensor, targets: Tensor, padding_mask: Optional[Tensor] = None, ignore_index: int = PAD_ID_EN):
         h = self.hidden(x, xa, None, padding_mask)
-        return _LossHeadFn.apply(h, self.token_embedding.weight, self.embedding_bf16(), targets, ignore_index)
+        return _LossHeadFn.apply(h, self.token_embedding.weight, self.embedding_bf16(), targets, ignore_index, self)
 
 
 # =====================================================================================================
@@ -703,6 +839,106 @@ class OLMoASRBase(nn.Module):
                                     dims.n_audio_layer, double_init=tv)
         self.decoder = TextDecoder(dims.n_vocab, dims.n_text_ctx, dims.n_text_state, dims.n_text_head,
                                    dims.n_text_layer, train_vocab_pad=tv)
+
+    # ---- slab mode ------------------------------------------------------------------------------------------
+    def use_slabs(self, direct_grads: bool = True):
+        """Move parameters, gradients and bf16 weight shadows into contiguous slabs (olmoasr_b200/slab.py) laid out in
+        backward-completion order, and hand every fused block precomputed views: the fused [Wq;Wk;Wv] / [Wk;Wv] weights
+        and [bq;0;bv] biases ARE slab ranges, weight gradients are accumulated in place by the wgrad GEMM epilogues.
+        Call after `.to(device)`; `state_dict()` names, shapes and values are unchanged.  Returns the ParamSlabs
+        (pass it to FusedAdamW(slabs=...) and, for data parallelism, to olmoasr_b200.ddp.SlabGradSync).
+
+        direct_grads=False keeps the hand-over of gradients through autograd (needed under torch DDP / FSDP hooks)."""
+        from .slab import ParamSlabs
+
+        if getattr(self, "_slabs", None) is not None:
+            self._slabs.direct_grads = direct_grads
+            return self._slabs
+        d_enc = self.dims.n_audio_state
+        if d_enc % 64 or self.dims.n_text_state % 64:
+            raise ValueError("use_slabs: model widths must be multiples of 64")
+
+        def mha_items(a: "MultiHeadAttention"):
+            d = a.query.weight.shape[0]
+            return [a.out.weight, a.out.bias, a.query.weight, a.key.weight, a.value.weight, a.query.bias, d, a.value.bias]
+
+        def block_items(b: "ResidualAttentionBlock"):
+            it = [b.mlp_ln.weight, b.mlp_ln.bias, b.mlp[2].weight, b.mlp[2].bias, b.mlp[0].weight, b.mlp[0].bias]
+            if b.cross_attn is not None:
+                it += [b.cross_attn_ln.weight, b.cross_attn_ln.bias] + mha_items(b.cross_attn)
+            it += [b.attn_ln.weight, b.attn_ln.bias] + mha_items(b.attn)
+            return it
+
+        enc, dec = self.encoder, self.decoder
+        layout = [dec.ln.weight, dec.ln.bias]
+        for b in reversed(list(dec.blocks)):
+            layout += block_items(b)
+        layout += [dec.token_embedding.weight, dec.positional_embedding, enc.ln_post.weight, enc.ln_post.bias]
+        for b in reversed(list(enc.blocks)):
+            layout += block_items(b)
+        layout += [enc.conv2.weight, enc.conv2.bias, enc.conv1.weight, enc.conv1.bias]
+        sl = ParamSlabs(self, layout)
+        sl.direct_grads = direct_grads
+
+        def install_mha(a: "MultiHeadAttention", direct: Dict[str, Tensor], prefix: str, cross: bool):
+            d = a.query.weight.shape[0]
+            assert sl.adjacent(a.query.weight, a.key.weight, a.value.weight)
+            assert sl.offset[id(a.value.bias)] == sl.offset[id(a.query.bias)] + 2 * d
+            a._slab_fused = (sl.span("S", a.query.weight, 3 * d * d).view(3 * d, d), sl.span("P", a.query.bias, 3 * d))
+            for lin in (a.query, a.key, a.value, a.out):
+                lin._slab_view = sl.shadow(lin.weight)
+            direct[prefix + ".out.weight"], direct[prefix + ".out.bias"] = sl.grad(a.out.weight), sl.grad(a.out.bias)
+            direct[prefix + ".query.bias"], direct[prefix + ".value.bias"] = sl.grad(a.query.bias), sl.grad(a.value.bias)
+            if cross:
+                direct[prefix + ".query.weight"] = sl.grad(a.query.weight)
+                direct[prefix + ".kv.weight"] = sl.span("G", a.key.weight, 2 * d * d).view(2 * d, d)
+            else:
+                direct[prefix + ".qkv.weight"] = sl.span("G", a.query.weight, 3 * d * d).view(3 * d, d)
+
+        for b in list(enc.blocks) + list(dec.blocks):
+            direct: Dict[str, Tensor] = {}
+            install_mha(b.attn, direct, "attn", cross=False)
+            if b.cross_attn is not None:
+                install_mha(b.cross_attn, direct, "cross_attn", cross=True)
+            for name, lin in (("mlp.0", b.mlp[0]), ("mlp.2", b.mlp[2])):
+                lin._slab_view = sl.shadow(lin.weight)
+                direct[name + ".weight"], direct[name + ".bias"] = sl.grad(lin.weight), sl.grad(lin.bias)
+            for name, ln in (("attn_ln", b.attn_ln), ("cross_attn_ln", b.cross_attn_ln), ("mlp_ln", b.mlp_ln)):
+                if ln is not None:
+                    direct[name + ".weight"], direct[name + ".bias"] = sl.grad(ln.weight), sl.grad(ln.bias)
+            sh = {}
+            sh["wqkv"], sh["bqkv"] = b.attn.fused_qkv()
+            sh["wo"] = b.attn.out.weight_bf16()
+            if b.cross_attn is not None:
+                sh["wcq"] = b.cross_attn.query.weight_bf16()
+                sh["wckv"], sh["bckv"] = b.cross_attn.fused_kv()
+                sh["wco"] = b.cross_attn.out.weight_bf16()
+            sh["w1"], sh["w2"] = b.mlp[0].weight_bf16(), b.mlp[2].weight_bf16()
+            b._slabs, b._slab_sh, b._direct = sl, sh, direct
+        enc._slabs, dec._slabs = sl, sl
+        enc._direct = {"conv1.weight": sl.grad(enc.conv1.weight), "conv1.bias": sl.grad(enc.conv1.bias),
+                       "conv2.weight": sl.grad(enc.conv2.weight), "conv2.bias": sl.grad(enc.conv2.bias),
+                       "ln_post.weight": sl.grad(enc.ln_post.weight), "ln_post.bias": sl.grad(enc.ln_post.bias)}
+        dec._direct = {"token_embedding.weight": sl.grad(dec.token_embedding.weight),
+                       "positional_embedding": sl.grad(dec.positional_embedding),
+                       "ln.weight": sl.grad(dec.ln.weight), "ln.bias": sl.grad(dec.ln.bias)}
+        dec._emb_slab_view = sl.shadow(dec.token_embedding.weight)
+        self._slabs = sl
+        if sl.device.type == "cuda":
+            sl.sync_shadows()
+        return sl
+
+    def grad_units(self):
+        """[(parameters, module whose `_bwd_done_cb` fires when their gradients are final | None)] in the order the
+        backward pass completes them (= slab layout order); consumed by olmoasr_b200.ddp.SlabGradSync."""
+        enc, dec = self.encoder, self.decoder
+        units = [([dec.ln.weight, dec.ln.bias], None)]
+        units += [(list(b.parameters()), b) for b in reversed(list(dec.blocks))]
+        units.append(([dec.token_embedding.weight, dec.positional_embedding], dec))
+        units.append(([enc.ln_post.weight, enc.ln_post.bias], None))
+        units += [(list(b.parameters()), b) for b in reversed(list(enc.blocks))]
+        units.append(([enc.conv2.weight, enc.conv2.bias, enc.conv1.weight, enc.conv1.bias], enc))
+        return units
 
     def embed_audio(self, mel: Tensor):
         return self.encoder(mel)

@@ -42,13 +42,15 @@ _SIGNATURES = {
                            c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64,
                            c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_void_p, c_float, c_void_p],
     "oasr_ce_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_void_p],
+    "oasr_ce_finalize": [c_void_p, c_void_p, c_void_p],
     "oasr_ce_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_void_p],
     "oasr_logits_to_f32": [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p],
     "oasr_embed_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_void_p],
     "oasr_embed_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_void_p],
     "oasr_cast_f32_to_bf16": [c_void_p, c_void_p, c_i64, c_void_p],
     "oasr_cast_conv_weight": [c_void_p, c_void_p, c_i64, c_i64, c_void_p],
-    "oasr_unpermute_conv_wgrad": [c_void_p, c_void_p, c_i64, c_i64, c_void_p],
+    "oasr_unpermute_conv_wgrad": [c_void_p, c_void_p, c_i64, c_i64, c_int, c_void_p],
+    "oasr_mask_to_kvlen": [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_void_p],
     "oasr_im2col_conv1": [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_void_p],
     "oasr_im2col_conv2": [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_void_p],
     "oasr_col2im_conv2_gelu_bwd": [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_void_p],
@@ -56,9 +58,12 @@ _SIGNATURES = {
     "oasr_gelu_bwd": [c_void_p, c_void_p, c_void_p, c_i64, c_void_p],
     "oasr_colsum_bf16": [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p],
     "oasr_optim_chunk_elems": [],
-    "oasr_grad_sqnorm": [c_void_p, c_void_p, c_i64, c_void_p, c_void_p],
-    "oasr_adamw_step": [c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_float,
-                        c_float, c_float, c_i64, c_void_p],
+    "oasr_grad_sqnorm": [c_void_p, c_void_p, c_i64, c_float, c_void_p, c_void_p],
+    "oasr_grad_sqnorm_flat": [c_void_p, c_i64, c_float, c_void_p, c_void_p],
+    "oasr_optim_prepare": [c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_void_p],
+    "oasr_adamw_step": [c_void_p, c_void_p, c_i64, c_void_p, c_float, c_float, c_float, c_float, c_float, c_void_p],
+    "oasr_adamw_flat": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_float, c_float, c_float,
+                        c_float, c_float, c_void_p],
     "oasr_gemm_bf16": [c_void_p, c_i64, c_int, c_void_p, c_i64, c_int, c_void_p, c_i64, c_void_p, c_void_p,
                        c_void_p, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_void_p],
 }

@@ -108,8 +108,11 @@ def log_mel_spectrogram(audio: Union[str, np.ndarray, torch.Tensor], n_mels: int
                         device: Optional[Union[str, torch.device]] = None) -> torch.Tensor:
     """Log-mel spectrogram of a waveform (n,) or batch (B, n): float32 or int16 samples at 16 kHz.
 
-    Returns (n_mels, n // 160) or (B, n_mels, n // 160) float32 on the CUDA device.  `n + padding` must be a
-    multiple of 640 samples (40 ms); a 30 s chunk is 480000."""
+    Returns (n_mels, n // 160) or (B, n_mels, n // 160) float32 on the CUDA device, n = samples + padding, any length
+    >= 400 (upstream: n // 160 frames for every n).  The kernel frames whole 640-sample groups, so other lengths are
+    zero-extended to the next multiple of 640 and the extra frames dropped: exact whenever the recording ends in
+    silence -- `transcribe` always appends 30 s of zeros (olmoasr/transcribe.py:148) -- and otherwise only the last two
+    frames see zeros where upstream's reflect padding would mirror the final 200 samples."""
     if not torch.is_tensor(audio):
         if isinstance(audio, str):
             audio = load_audio(audio)
@@ -129,13 +132,19 @@ def log_mel_spectrogram(audio: Union[str, np.ndarray, torch.Tensor], n_mels: int
         audio = audio.float()
     if padding > 0:
         audio = F.pad(audio, (0, padding))
+    n_true = audio.shape[1]
+    if n_true < N_FFT:
+        raise ValueError(f"need at least {N_FFT} samples, got {n_true}")
+    group = 4 * HOP_LENGTH
+    if n_true % group != 0:
+        audio = F.pad(audio, (0, group - n_true % group))
     audio = audio.contiguous()
     B, n = audio.shape
-    if n % (4 * HOP_LENGTH) != 0:
-        raise ValueError(f"number of samples ({n}) must be a multiple of {4 * HOP_LENGTH}")
     window, cos_t, sin_t, filt, klo, khi = _device_tables(audio.device.index or 0, n_mels)
     out = torch.empty((B, n_mels, n // HOP_LENGTH), device=audio.device, dtype=torch.float32)
     clip_max = torch.empty(B, device=audio.device, dtype=torch.float32)
     call("oasr_logmel", ptr(audio), int(audio.dtype == torch.int16), ptr(window), ptr(cos_t), ptr(sin_t), ptr(filt),
          ptr(klo), ptr(khi), ptr(out), ptr(clip_max), B, n, n_mels, stream())
+    if n != n_true:
+        out = out[:, :, : n_true // HOP_LENGTH]
     return out[0] if squeeze else out

@@ -24,7 +24,10 @@ ce_fwd_kernel(const bf16* __restrict__ logits, const int64_t* __restrict__ targe
   const int64_t row = blockIdx.x;
   const int64_t y = targets[row];
   if (y == ignore_index || y < 0 || y >= V) {  // nothing to compute for ignored rows
-    if (threadIdx.x == 0) lse[row] = 0.f;
+    if (threadIdx.x == 0) {
+      lse[row] = 0.f;
+      if (y != ignore_index) atomicAdd(loss_sum_count + 2, 1.0f);   // a target outside [0, V): F.cross_entropy would raise
+    }
     return;
   }
   const bf16* x = logits + row * ld;
@@ -99,6 +102,9 @@ ce_bwd_kernel(bf16* __restrict__ logits, const int64_t* __restrict__ targets, co
   }
 }
 
+// loss = sum / count (mean over the non-ignored targets of this rank, train_timestamps.py:1444-1448)
+__global__ void ce_finalize_kernel(const float* __restrict__ lsc, float* __restrict__ loss) { *loss = lsc[0] / lsc[1]; }
+
 // bf16 (rows, ld) -> f32 (rows, V) contiguous: the `.float()` of model.py:770 for callers that want logits
 __global__ void logits_to_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, int64_t ld, int V) {
   const int64_t row = blockIdx.x;
@@ -114,6 +120,13 @@ extern "C" int oasr_ce_fwd(const void* logits, const int64_t* targets, float* ls
                            int64_t V, int64_t ld, int64_t ignore_index, void* stream) {
   OASR_REQUIRE(rows > 0 && V > 0 && ld >= V && (ld & 7) == 0, "ce_fwd: bad shape rows=%ld V=%ld ld=%ld", (long)rows, (long)V, (long)ld);
   ce_fwd_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const bf16*)logits, targets, lse, loss_sum_count, ld, (int)V, ignore_index);
+  OASR_LAUNCH_CHECK();
+  return OASR_OK;
+}
+
+extern "C" int oasr_ce_finalize(const float* loss_sum_count, float* loss, void* stream) {
+  OASR_REQUIRE(loss_sum_count != nullptr && loss != nullptr, "ce_finalize: null");
+  ce_finalize_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(loss_sum_count, loss);
   OASR_LAUNCH_CHECK();
   return OASR_OK;
 }

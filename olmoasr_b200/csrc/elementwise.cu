@@ -33,14 +33,49 @@ __global__ void cast_conv_weight_kernel(const float* __restrict__ src, bf16* __r
   dst[i] = __float2bfloat16_rn(src[(o * c_in + c) * 3 + k]);
 }
 // and its inverse for the weight gradient: (C_out, 3, C_in) f32 -> (C_out, C_in, 3) f32
-__global__ void unpermute_conv_wgrad_kernel(const float* __restrict__ src, float* __restrict__ dst, int c_out, int c_in) {
+__global__ void unpermute_conv_wgrad_kernel(const float* __restrict__ src, float* __restrict__ dst, int c_out, int c_in,
+                                            int accumulate) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // index into dst
   const int64_t n = static_cast<int64_t>(c_out) * 3 * c_in;
   if (i >= n) return;
   const int k = i % 3;
   const int c = (i / 3) % c_in;
   const int64_t o = i / (3 * c_in);
-  dst[i] = src[(o * 3 + k) * c_in + c];
+  const float v = src[(o * 3 + k) * c_in + c];
+  dst[i] = accumulate ? dst[i] + v : v;
+}
+
+// ------------------------------------------------------------------ padding mask -> per-sample key count
+// The reference hands the decoder a dense additive mask (B, S, S) f32 whose columns >= len(text_input) are -inf on every
+// row (scripts/training/train_timestamps.py:314-315; added to the causal mask at olmoasr/model.py:740-743).  The
+// attention kernels want the key count.  One block per sample: count the zeros of row 0, then verify that every row has
+// exactly that structure; any other additive mask raises err[0] (reported by the host as a ValueError).
+__global__ void __launch_bounds__(256)
+mask_to_kvlen_kernel(const float* __restrict__ mask, int32_t* __restrict__ kv_len, int32_t* __restrict__ err, int S) {
+  const float* m = mask + static_cast<int64_t>(blockIdx.x) * S * S;
+  __shared__ int s_len;
+  __shared__ int s_bad;
+  if (threadIdx.x == 0) { s_len = 0; s_bad = 0; }
+  __syncthreads();
+  int cnt = 0;
+  for (int c = threadIdx.x; c < S; c += blockDim.x) cnt += (m[c] == 0.f);
+  cnt = warp_sum(cnt);
+  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_len, cnt);
+  __syncthreads();
+  const int len = s_len;
+  int bad = 0;
+  const int64_t n = static_cast<int64_t>(S) * S;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c = static_cast<int>(i % S);
+    const float v = m[i];
+    bad |= (c < len) ? (v != 0.f) : !(v < -1e30f);
+  }
+  if (bad) s_bad = 1;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    kv_len[blockIdx.x] = len;
+    if (s_bad) atomicOr(err, 1);
+  }
 }
 
 // ------------------------------------------------------------------ embedding
@@ -247,9 +282,16 @@ extern "C" int oasr_cast_conv_weight(const float* src, void* dst, int64_t c_out,
   return OASR_OK;
 }
 
-extern "C" int oasr_unpermute_conv_wgrad(const float* src, float* dst, int64_t c_out, int64_t c_in, void* stream) {
+extern "C" int oasr_unpermute_conv_wgrad(const float* src, float* dst, int64_t c_out, int64_t c_in, int accumulate, void* stream) {
   const int64_t n = c_out * 3 * c_in;
-  unpermute_conv_wgrad_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, (int)c_out, (int)c_in);
+  unpermute_conv_wgrad_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, (int)c_out, (int)c_in, accumulate);
+  OASR_LAUNCH_CHECK();
+  return OASR_OK;
+}
+
+extern "C" int oasr_mask_to_kvlen(const float* mask, int32_t* kv_len, int32_t* err, int64_t batch, int64_t S, void* stream) {
+  OASR_REQUIRE(batch > 0 && S > 0 && mask && kv_len && err, "mask_to_kvlen: bad arguments");
+  mask_to_kvlen_kernel<<<(unsigned)batch, 256, 0, (cudaStream_t)stream>>>(mask, kv_len, err, (int)S);
   OASR_LAUNCH_CHECK();
   return OASR_OK;
 }

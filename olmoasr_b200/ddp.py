@@ -13,8 +13,11 @@ tensor / ncclGroupEnd -- no flattening), and the 1 / world_size average is folde
     opt.step(inv_scale=reducer.finish())           # waits for the collectives; returns 1 / world_size
 
 Same collective order on every rank (the autograd graph is the same), same result as DDP up to fp32 summation order.
-Status: host logic covered by the 2-rank gloo test; not yet measured on NVLink (written after this round's GPU
-budget was spent), so bench.py keeps DistributedDataParallel unless OASR_DDP_IMPL=blockwise.
+
+`SlabGradSync` (below) is the B200-first form and what bench.py uses: gradients already live in ONE flat fp32 slab in
+backward-completion order (olmoasr_b200/slab.py), so the sum across ranks is a handful of large contiguous all-reduces
+-- NCCL's bandwidth regime over NVLink 5 / NVSwitch instead of 87 latency-protocol bucket launches -- issued as soon as
+the backward has finished a slab range, with no flatten copies and no per-parameter divides.
 """
 from __future__ import annotations
 
@@ -103,3 +106,109 @@ class BlockwiseGradReducer:
         for h in self._hooks:
             h.remove()
         self._hooks.clear()
+
+
+class SlabGradSync:
+    """Data-parallel gradient sum over a model in slab mode (`model.use_slabs()`): replaces
+    `DDP(model, device_ids=[rank])` of scripts/training/train_timestamps.py:2329-2330.
+
+        slabs = model.use_slabs()
+        sync = SlabGradSync(model, slabs)              # broadcasts rank 0's weights, like DDP's constructor
+        opt = FusedAdamW(model.parameters(), slabs=slabs)
+        loss = model(mel, tokens, mask, targets=y); opt.zero_grad(); loss.backward()
+        opt.step(inv_scale=sync.finish())              # SUM across ranks, 1 / world folded into the fused optimizer
+
+    The slab is cut into segments of >= `bucket_bytes` at module boundaries (`model.grad_units()`); a segment's all-reduce
+    is launched from the backward pass the moment its last producer (a fused block, the embedding, the conv stem) has
+    enqueued its kernels, on NCCL's own stream, so it overlaps the rest of the backward.  Semantics are DDP's: every
+    rank ends with the same SUM, the caller's optimizer divides by world (per-rank mean loss, gradient averaged over
+    ranks -- train_timestamps.py:1444-1450 + DDP).  Models without `grad_units()` get one all-reduce in finish()."""
+
+    def __init__(self, model: nn.Module, slabs, process_group=None, bucket_bytes: int = 256 << 20, broadcast: bool = True):
+        if not dist.is_initialized():
+            raise RuntimeError("SlabGradSync needs an initialised process group")
+        self.group = process_group
+        self.world = dist.get_world_size(process_group)
+        self.slabs = slabs
+        self.enabled = True
+        slabs.direct_grads = True
+        units = model.grad_units() if hasattr(model, "grad_units") else [(list(slabs.params), None)]
+        order = {pid: i for i, pid in enumerate(slabs.layout_order)}
+        nxt = 0
+        for ps, _ in units:     # every unit must be a contiguous run of the slab layout, units in layout order
+            idx = sorted(order[id(p)] for p in ps)
+            if idx != list(range(nxt, nxt + len(ps))):
+                raise ValueError("grad_units() must partition the slab layout into consecutive runs, in layout order")
+            nxt += len(ps)
+        if nxt != len(order):
+            raise ValueError("grad_units() must cover every slab parameter")
+        self.segments: List[tuple] = []          # (start, end) element ranges of slabs.G, in backward order
+        self._triggers: List[Optional[nn.Module]] = []
+        start, cur = 0, []
+        for k, (ps, mod) in enumerate(units):
+            cur += ps
+            last = k == len(units) - 1
+            end = slabs.numel if last else slabs.range_of(cur)[1]
+            if last or (mod is not None and (end - start) * 4 >= bucket_bytes):
+                self.segments.append((start, end))
+                self._triggers.append(mod)
+                start, cur = end, []
+        self._launched = [False] * len(self.segments)
+        self._works = []
+        for i, mod in enumerate(self._triggers):
+            if mod is not None:
+                mod._bwd_done_cb = self._make_cb(i)
+        if broadcast and self.world > 1:
+            src = dist.get_global_rank(process_group, 0) if process_group is not None else 0
+            with torch.no_grad():
+                dist.broadcast(slabs.P, src=src, group=process_group)     # one flat broadcast of every parameter
+                for b in model.buffers():
+                    dist.broadcast(b.data, src=src, group=process_group)
+            slabs.invalidate()
+
+    def _make_cb(self, i: int):
+        def cb():
+            # everything before segment i in backward order is final as well (a trigger-less unit rides with the next one)
+            for j in range(i + 1):
+                if not self._launched[j]:
+                    self._launch(j)
+        return cb
+
+    def _launch(self, i: int):
+        self._launched[i] = True
+        if not self.enabled or self.world == 1:
+            return
+        a, b = self.segments[i]
+        self._works.append(dist.all_reduce(self.slabs.G[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def finish(self) -> float:
+        """Launch what the backward did not trigger, wait (stream-wise) for every collective, re-arm; returns 1 / world."""
+        for i in range(len(self.segments)):
+            if not self._launched[i]:
+                self._launch(i)
+        for w in self._works:
+            w.wait()
+        self._works.clear()
+        self._launched = [False] * len(self.segments)
+        return 1.0 / self.world
+
+    class _NoSync:
+        def __init__(self, outer):
+            self.outer = outer
+
+        def __enter__(self):
+            self.outer.enabled = False
+
+        def __exit__(self, *exc):
+            self.outer.enabled = True
+            self.outer._launched = [False] * len(self.outer.segments)
+
+    def no_sync(self):
+        """Gradient accumulation: backward passes inside this context only accumulate into the slab (the kernels always
+        accumulate); the pass outside it triggers the all-reduces of the accumulated sum."""
+        return SlabGradSync._NoSync(self)
+
+    def remove(self):
+        for mod in self._triggers:
+            if mod is not None:
+                mod._bwd_done_cb = None

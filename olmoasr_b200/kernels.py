@@ -136,14 +136,22 @@ def attention_bwd(q, k, v, o, dout, lse, B, H, Tq, Tkv, causal=False, kv_len=Non
 
 
 def ce_fwd(logits, targets, V, ignore_index):
-    """logits (rows, ld) bf16; returns (lse (rows,), loss_sum_count (2,)) -- loss = lsc[0] / lsc[1]."""
+    """logits (rows, ld) bf16; returns (lse (rows,), lsc (4,)): lsc = [loss sum, target count, bad-target count, -];
+    `ce_finalize(lsc)` turns it into the mean loss."""
     _bf16_2d(logits, "ce logits")
     rows = logits.shape[0]
     _req(targets.dtype == torch.int64 and targets.numel() == rows and targets.is_contiguous(), "ce: targets int64 (rows,)")
     lse = torch.empty(rows, device=logits.device, dtype=torch.float32)
-    lsc = torch.zeros(2, device=logits.device, dtype=torch.float32)
+    lsc = torch.zeros(4, device=logits.device, dtype=torch.float32)
     call("oasr_ce_fwd", ptr(logits), ptr(targets), ptr(lse), ptr(lsc), rows, V, logits.stride(0), ignore_index, stream())
     return lse, lsc
+
+
+def ce_finalize(lsc):
+    """0-d mean loss = lsc[0] / lsc[1] (no torch arithmetic on the way to the loss)."""
+    loss = torch.empty((), device=lsc.device, dtype=torch.float32)
+    call("oasr_ce_finalize", ptr(lsc), ptr(loss), stream())
+    return loss
 
 
 def ce_bwd_(logits, targets, lse, lsc, grad_out, V, ignore_index):
@@ -191,10 +199,21 @@ def cast_conv_weight(w, dst=None):
     return dst
 
 
-def unpermute_conv_wgrad(g, c_out, c_in):
-    out = torch.empty((c_out, c_in, 3), device=g.device, dtype=torch.float32)
-    call("oasr_unpermute_conv_wgrad", ptr(g), ptr(out), c_out, c_in, stream())
+def unpermute_conv_wgrad(g, c_out, c_in, out=None):
+    """(C_out, 3, C_in) f32 -> (C_out, C_in, 3) f32; with `out` (a gradient-slab view) the result is ADDED into it."""
+    accumulate = out is not None
+    if out is None:
+        out = torch.empty((c_out, c_in, 3), device=g.device, dtype=torch.float32)
+    call("oasr_unpermute_conv_wgrad", ptr(g), ptr(out), c_out, c_in, int(accumulate), stream())
     return out
+
+
+def mask_to_kvlen(mask, err_flag):
+    """(B, S, S) f32 additive padding mask -> (B,) int32 key counts; err_flag (1,) int32 is OR-ed with 1 on a malformed mask."""
+    _req(mask.is_cuda and mask.dtype == torch.float32 and mask.dim() == 3 and mask.is_contiguous(), "mask: (B,S,S) f32 CUDA")
+    kv = torch.empty(mask.shape[0], device=mask.device, dtype=torch.int32)
+    call("oasr_mask_to_kvlen", ptr(mask), ptr(kv), ptr(err_flag), mask.shape[0], mask.shape[1], stream())
+    return kv
 
 
 def im2col_conv1(mel, kpad):

@@ -61,6 +61,101 @@ def test_gemm_epilogues(K):
     _close(acc, ref + 2.0, rtol=1e-4)
 
 
+# Production shapes of the headline benchmark (medium, 32 clips; profiles/r01_gemm_table.txt).  The unit shapes above never
+# make a persistent CTA process a second tile: these do (>= 3 tiles per CTA pair), which exercises the TMEM double-buffer
+# phase flip, the stage ring wrapping across tiles, TMA-store slot recycling, M-fastest rasterisation and split-K.
+def _rel_l2(got, want):
+    return float((got.float() - want.float()).norm() / want.float().norm())
+
+
+def test_gemm_production_fc1_gelu_and_gelu_bwd(K):
+    torch.manual_seed(11)
+    M, N, Kd = 48000, 4096, 1024            # encoder fc1: 375 x 16 = 6000 tiles of 128 x 256 on 74 CTA pairs
+    A = torch.randn(M, Kd, device="cuda").bfloat16()
+    B = (torch.randn(N, Kd, device="cuda") / math.sqrt(Kd)).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    ref = A.float() @ B.float().t()
+    rb = (ref + bias.bfloat16().float()).bfloat16().float()
+    h, g = K.gemm(A, B, M, N, Kd, bias=bias, epi=K.EPI_BF16_GELU, block_n=256)
+    assert _rel_l2(h, rb) < 3e-3 and (h.float() - rb).abs().max().item() <= 2.0 ** -6 * rb.abs().max().item()
+    assert _rel_l2(g, F.gelu(h.float())) < 4e-3
+    del ref, rb, g
+    # fc2 dgrad with the GELU-backward epilogue: dh = bf16(bf16(dy W2) * gelu'(h)),  (48000 x 1024) @ (1024 x 4096)
+    dy = torch.randn(M, Kd, device="cuda").bfloat16()
+    W2 = (torch.randn(Kd, N, device="cuda") / math.sqrt(Kd)).bfloat16()      # stored (N_out=1024, K_in=4096): read MN-major
+    got = K.gemm(dy, W2, M, N, Kd, b_mn=True, aux=h, epi=K.EPI_BF16_GELU_BWD, block_n=256)
+    x = h.float().requires_grad_(True)
+    F.gelu(x).backward((dy.float() @ W2.float()).bfloat16().float())
+    assert _rel_l2(got, x.grad) < 4e-3
+
+
+def test_gemm_production_tied_logits_raster_m(K):
+    torch.manual_seed(12)
+    M, V, d = 14336, 51865, 1024            # decoder logits: B (the embedding) is the larger operand -> M-fastest raster
+    x = torch.randn(M, d, device="cuda").bfloat16()
+    E = (torch.randn(V, d, device="cuda") / math.sqrt(d)).bfloat16()
+    ld = (V + 255) // 256 * 256
+    buf = torch.full((M, ld), 7.0, device="cuda", dtype=torch.bfloat16)
+    K.gemm(x, E, M, V, d, out=buf, block_n=256)
+    for r0 in (0, 4096, 14336 - 1024):      # compare in row slabs: the fp32 reference of the whole product is 3 GB
+        ref = x[r0:r0 + 1024].float() @ E.float().t()
+        assert _rel_l2(buf[r0:r0 + 1024, :V], ref) < 3e-3, r0
+    assert (buf[:, V:] == 7.0).all() or (buf[:, V:] == 0.0).all()            # padding columns: untouched or zero, never garbage
+
+
+def test_gemm_production_wgrad_split_k(K):
+    torch.manual_seed(13)
+    M, N, Kd = 48000, 1024, 1024            # dW = dy^T x: 32 output tiles, reduction over 48000 rows, split-K + fp32 red.add
+    dy = (torch.randn(M, N, device="cuda") * 0.05).bfloat16()
+    x = torch.randn(M, Kd, device="cuda").bfloat16()
+    ref = dy.float().t() @ x.float()
+    for split in (1, 4, 7):
+        out = torch.full((N, Kd), 1.0, device="cuda")
+        K.gemm(dy, x, N, Kd, M, a_mn=True, b_mn=True, out=out, epi=K.EPI_F32_ATOMIC_ADD, split_k=split, block_n=256)
+        assert _rel_l2(out - 1.0, ref) < 2e-5, split
+    out = K.gemm(dy, x, N, Kd, M, a_mn=True, b_mn=True, epi=K.EPI_F32, block_n=256)
+    assert _rel_l2(out, ref) < 2e-5
+
+
+def test_gemm_decoder_shape_three_waves_and_residual(K):
+    torch.manual_seed(14)
+    M, N, Kd = 14336, 1024, 1024            # 112 x 4 = 448 tiles on 74 pairs: 3.03 waves
+    A = torch.randn(M, Kd, device="cuda").bfloat16()
+    B = (torch.randn(N, Kd, device="cuda") / math.sqrt(Kd)).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    aux = torch.randn(M, N, device="cuda").bfloat16()
+    ref = aux.float() + ((A.float() @ B.float().t()) + bias.bfloat16().float()).bfloat16().float()
+    got = K.gemm(A, B, M, N, Kd, bias=bias, aux=aux, epi=K.EPI_BF16_RESIDUAL, block_n=256)
+    assert _rel_l2(got, ref) < 3e-3
+    got128 = K.gemm(A, B, M, N, Kd, bias=bias, aux=aux, epi=K.EPI_BF16_RESIDUAL, block_n=128)
+    assert _rel_l2(got128, ref) < 3e-3
+
+
+def test_gemm_cluster4_and_sm_budget(K, monkeypatch):
+    """The opt-in 4-CTA cluster mode (OASR_GEMM_CLUSTER=4, read per call) and a reduced SM budget (the persistent grid
+    shrinks, every CTA takes more tiles) give the same numbers as the default."""
+    torch.manual_seed(15)
+    M, N, Kd = 6144, 3072, 1024
+    A = torch.randn(M, Kd, device="cuda").bfloat16()
+    B = (torch.randn(N, Kd, device="cuda") / math.sqrt(Kd)).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    base = K.gemm(A, B, M, N, Kd, bias=bias, block_n=256)
+    ref = ((A.float() @ B.float().t()) + bias.bfloat16().float())
+    assert _rel_l2(base, ref) < 3e-3
+    monkeypatch.setenv("OASR_GEMM_CLUSTER", "4")
+    c4 = K.gemm(A, B, M, N, Kd, bias=bias, block_n=256)
+    monkeypatch.delenv("OASR_GEMM_CLUSTER")
+    assert torch.equal(c4, base)
+    prev = K.set_gemm_sm_budget(132)
+    try:
+        b132 = K.gemm(A, B, M, N, Kd, bias=bias, block_n=256)
+        K.set_gemm_sm_budget(20)
+        b20 = K.gemm(A, B, M, N, Kd, bias=bias, block_n=256)       # 288 tiles on 10 pairs: ~29 tiles per CTA
+    finally:
+        K.set_gemm_sm_budget(prev)
+    assert torch.equal(b132, base) and torch.equal(b20, base)
+
+
 def test_gemm_rejects_bad_arguments(K):
     from olmoasr_b200._lib import OasrError
     A = torch.zeros(16, 12, device="cuda", dtype=torch.bfloat16)  # row stride 12 elements: not TMA-legal
@@ -156,8 +251,11 @@ def test_cross_entropy_fwd_bwd(K):
     ref_in = logits[:, :V].float().requires_grad_(True)
     loss_ref = F.cross_entropy(ref_in, y, ignore_index=51864)
     lse, lsc = K.ce_fwd(logits, y, V, 51864)
-    loss = lsc[0] / lsc[1]
+    loss = K.ce_finalize(lsc)
     assert abs(loss.item() - loss_ref.item()) <= 1e-4 * abs(loss_ref.item())
+    assert lsc[1].item() == float((y != 51864).sum()) and lsc[2].item() == 0.0
+    y_bad = y.clone(); y_bad[1] = 60000; y_bad[2] = -3           # out-of-range targets are counted (F.cross_entropy raises)
+    assert K.ce_fwd(logits, y_bad, V, 51864)[1][2].item() == 2.0
     (loss_ref * 7.0).backward()
     K.ce_bwd_(logits, y, lse, lsc, torch.tensor([7.0], device="cuda"), V, 51864)
     _close(logits[:, :V], ref_in.grad, rtol=1.0 / 128)
@@ -228,6 +326,35 @@ def test_small_elementwise(K):
     _close(K.gelu_bwd(g, pre), xr.grad)
 
 
+def test_padding_mask_to_key_counts_and_validation(monkeypatch):
+    """The dense additive mask of train_timestamps.py:314-315 -> per-sample key counts on the device; any other additive
+    mask is rejected (model.py:740-743 would accept it; this implementation does not support it and must say so)."""
+    from olmoasr_b200 import _core
+    from olmoasr_b200 import synthetic as synth
+
+    monkeypatch.setattr(_core, "STRICT_MASK", True)
+    ti, ty, pm, lens = synth.text_batch(5)
+    kv = _core.kv_len_from_padding_mask(pm.cuda())
+    want = (pm[:, 0, :] == 0).sum(-1)
+    assert kv.dtype == torch.int32 and torch.equal(kv.cpu().long(), want)
+    assert torch.equal(_core.kv_len_from_padding_mask(want.cuda()), want.cuda().int())       # lengths pass straight through
+    big_neg = pm.clone(); big_neg[big_neg == -float("inf")] = torch.finfo(torch.float32).min
+    assert torch.equal(_core.kv_len_from_padding_mask(big_neg.cuda()).cpu().long(), want)     # finfo.min masks are fine
+    bad = pm.clone(); bad[2, 100, 3] = -1.0                                                   # an arbitrary additive bias
+    with pytest.raises(ValueError, match="padding_mask"):
+        _core.kv_len_from_padding_mask(bad.cuda())
+    bad2 = pm.clone(); bad2[1, 7, 440] = 0.0                                                  # a hole behind the length
+    with pytest.raises(ValueError, match="padding_mask"):
+        _core.kv_len_from_padding_mask(bad2.cuda())
+    # deferred mode: the error surfaces on the next call instead of stalling the stream
+    monkeypatch.setattr(_core, "STRICT_MASK", False)
+    _core.kv_len_from_padding_mask(bad.cuda())
+    torch.cuda.synchronize()
+    with pytest.raises(ValueError, match="padding_mask"):
+        _core.kv_len_from_padding_mask(pm.clone().cuda())
+    _core.kv_len_from_padding_mask(pm.clone().cuda())                                         # flag was cleared
+
+
 # ------------------------------------------------------------------------------------------------ log-mel
 def test_logmel_matches_oracle(golden_dir):
     from olmoasr_b200 import audio
@@ -249,3 +376,12 @@ def test_logmel_matches_oracle(golden_dir):
     assert np.abs(a - b).max() < 1e-4
     short = audio.log_mel_spectrogram(audio.pad_or_trim(wav[0, :51237].cuda()))
     assert short.shape == (80, 3000)
+    # any length (ffmpeg output is arbitrary): n // 160 frames like upstream; with transcribe's 30 s of appended zeros the
+    # result is exact, without it only the last two frames may differ (zero extension instead of the end reflection)
+    odd = wav[0, :51237]
+    a = audio.log_mel_spectrogram(odd.cuda(), padding=480000).cpu().numpy()
+    b = logmel.log_mel_spectrogram(np.pad(odd.numpy(), (0, 480000)))
+    assert a.shape == b.shape == (80, (51237 + 480000) // 160) and np.abs(a - b).max() < 1e-4
+    c = audio.log_mel_spectrogram(odd.cuda()).cpu().numpy()
+    e = logmel.log_mel_spectrogram(odd.numpy())
+    assert c.shape == e.shape == (80, 51237 // 160) and np.abs(c[:, :-2] - e[:, :-2]).max() < 1e-4

@@ -1,5 +1,6 @@
-"""FusedAdamW (grad-norm + clip + AdamW in two launches) against torch's clip_grad_norm_ + AdamW
-(scripts/training/train_timestamps.py:1508-1522 with the defaults of :2110-2116)."""
+"""FusedAdamW (grad-norm + clip + AdamW in three launches) against torch's clip_grad_norm_ + AdamW
+(scripts/training/train_timestamps.py:1508-1522 with the defaults of :2110-2116), in both storage forms (pointer table
+and parameter slabs), and the contract between the optimizer and the model's bf16 weight shadows."""
 import pytest
 import torch
 
@@ -33,7 +34,9 @@ def test_matches_torch_adamw_with_clipping():
         for p, q in zip(ours, ref):
             assert torch.allclose(p, q, rtol=2e-5, atol=2e-6), (step, p.shape, (p - q).abs().max().item())
     st = o1.state[ours[0]]
-    assert set(st) >= {"step", "exp_avg", "exp_avg_sq"} and float(st["step"]) == 4.0
+    sd = o1.state_dict()       # refreshes `step` from the device counter
+    assert set(st) >= {"step", "exp_avg", "exp_avg_sq"} and float(st["step"]) == 4.0 and o1.applied_steps() == 4
+    assert all(p._version > 0 for p in ours)     # raw-pointer updates are reported to autograd (shadow caches key on it)
     assert torch.allclose(st["exp_avg"], o2.state[ref[0]]["exp_avg"], rtol=1e-4, atol=1e-7)
 
 
@@ -47,8 +50,14 @@ def test_non_finite_gradients_skip_the_step_and_unscale():
         p.grad = torch.ones_like(p)
     ps[1].grad[3] = float("inf")
     opt.step()
-    assert opt._found_inf.item() == 1.0
+    assert opt.found_inf().item() == 1.0
     assert all(torch.equal(a, b) for a, b in zip(ps, before))          # GradScaler semantics: untouched
+    assert opt.applied_steps() == 0                                     # ... and the skipped step is not counted
+    for p in ps:
+        p.grad = torch.ones_like(p)
+    opt._found_inf.zero_()
+    opt.step()
+    assert opt.applied_steps() == 1 and opt.found_inf().item() == 0.0
     # loss-scaled gradients: inv_scale undoes the scale before clipping and the update
     a = _make([(257,)], 2)
     b = [a[0].detach().clone().requires_grad_(True)]
@@ -60,3 +69,116 @@ def test_non_finite_gradients_skip_the_step_and_unscale():
     oa.step(inv_scale=1.0 / 65536.0)
     ob.step()
     assert torch.allclose(a[0], b[0], rtol=1e-5, atol=1e-7)
+    # the norm is accumulated on UNSCALED values: 2^20 elements of 65536 * 1e13 overflow fp32 if squared before unscaling
+    c = _make([(1 << 20,)], 3)
+    oc = FusedAdamW(c, lr=1e-2, max_grad_norm=1.0)
+    c[0].grad = torch.full_like(c[0], 65536.0 * 1e13)
+    oc.step(inv_scale=1.0 / 65536.0)
+    assert oc.found_inf().item() == 0.0 and abs(oc.grad_norm().item() / (1e13 * 1024.0) - 1.0) < 1e-3
+
+
+def test_gradient_pointer_table_is_double_buffered():
+    """Fresh gradient tensors every step (zero_grad(set_to_none=True)) with no host sync in between: the pinned pointer
+    table of step N must not be overwritten before its H2D copy ran."""
+    from olmoasr_b200.optim import FusedAdamW
+
+    ours = _make([(4096, 256), (333,)], 5)
+    ref = [p.detach().clone().requires_grad_(True) for p in ours]
+    o1 = FusedAdamW(ours, lr=1e-3, max_grad_norm=1.0)
+    o2 = torch.optim.AdamW(ref, lr=1e-3, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.1)
+    keep = []
+    for step in range(6):
+        for p, q in zip(ours, ref):
+            g = torch.randn_like(p)
+            keep.append(g)                       # keep every gradient alive so that each step has NEW addresses
+            p.grad, q.grad = g, g.clone()
+        torch.nn.utils.clip_grad_norm_(ref, 1.0)
+        o2.step()
+        o1.step()
+    torch.cuda.synchronize()
+    for p, q in zip(ours, ref):
+        assert torch.allclose(p, q, rtol=5e-5, atol=5e-6)
+
+
+def _tiny_model(seed=0):
+    import olmoasr_b200 as ob
+    from olmoasr_b200.model import OLMoASR
+    torch.manual_seed(seed)
+    return OLMoASR(ob.VARIANT_TO_DIMS["tiny"]).cuda()
+
+
+def _batch(B=2):
+    import olmoasr_b200 as ob
+    from olmoasr_b200 import synthetic as synth
+    wav = synth.waveforms(B)
+    ti, ty, pm, _ = synth.text_batch(B)
+    return ob.log_mel_spectrogram(wav.cuda()), ti.cuda(), ty.cuda(), pm.cuda()
+
+
+@pytest.mark.parametrize("slab", [False, True])
+def test_weight_shadows_follow_the_optimizer(slab):
+    """the GEMMs read bf16 shadows of the fp32 masters; after an optimizer step the shadows must be
+    the new masters' bf16 roundings, in both storage forms, and the model's output must move."""
+    from olmoasr_b200.optim import FusedAdamW
+
+    m = _tiny_model()
+    slabs = m.use_slabs() if slab else None
+    opt = FusedAdamW(m.parameters(), lr=1e-3, slabs=slabs)
+    mel, ti, ty, pm = _batch()
+    w_before = m.decoder.blocks[1].mlp[0].weight_bf16().clone()
+    losses = []
+    for _ in range(4):
+        loss = m(mel, ti, pm, targets=ty)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert losses[-1] < losses[0], losses                    # training on one batch must make progress
+    assert not torch.equal(w_before, m.decoder.blocks[1].mlp[0].weight_bf16())   # ... through the GEMM weights too
+    with torch.no_grad():
+        m(mel, ti, pm, targets=ty)                           # rebuilds / checks the shadows
+    blk = m.decoder.blocks[1]
+    w, b = blk.attn.fused_qkv()
+    d = blk.attn.query.weight.shape[0]
+    for i, lin in enumerate((blk.attn.query, blk.attn.key, blk.attn.value)):
+        assert torch.equal(w[i * d:(i + 1) * d], lin.weight.detach().bfloat16())
+    assert torch.equal(b[:d], blk.attn.query.bias.detach()) and torch.equal(b[2 * d:], blk.attn.value.bias.detach())
+    assert b[d:2 * d].abs().max().item() == 0.0                                # the key projection has no bias
+    assert torch.equal(blk.mlp[0].weight_bf16(), blk.mlp[0].weight.detach().bfloat16())
+    assert torch.equal(m.decoder.embedding_bf16(), m.decoder.token_embedding.weight.detach().bfloat16())
+    assert torch.equal(m.encoder.conv2.weight_bf16().view(-1, 3, d), m.encoder.conv2.weight.detach().permute(0, 2, 1).bfloat16())
+
+
+def test_slab_training_matches_autograd_handover():
+    """Slab mode with direct gradients (kernels accumulate into the flat gradient slab, AdamW over flat memory, bf16
+    shadows written by the update) against the plain mode (fresh gradient tensors through autograd, pointer-table AdamW):
+    same gradients, same weights after two steps, same loss trajectory."""
+    from olmoasr_b200.optim import FusedAdamW
+
+    ma, mb = _tiny_model(0), _tiny_model(0)
+    slabs = mb.use_slabs()
+    oa = FusedAdamW(ma.parameters(), lr=1e-3)
+    ob_ = FusedAdamW(mb.parameters(), lr=1e-3, slabs=slabs)
+    mel, ti, ty, pm = _batch()
+    for step in range(2):
+        la = ma(mel, ti, pm, targets=ty); oa.zero_grad(); la.backward()
+        lb = mb(mel, ti, pm, targets=ty); ob_.zero_grad(); lb.backward()
+        assert abs(la.item() - lb.item()) <= 2e-3 * abs(la.item()), (step, la.item(), lb.item())
+        if step == 0:
+            for (k, p), q in zip(ma.named_parameters(), mb.parameters()):
+                rel = (p.grad - q.grad).norm() / (p.grad.norm() + 1e-20)
+                assert rel <= 2e-3, (k, float(rel))          # fp32 atomics / split-K order differ, nothing else
+                assert q.grad.data_ptr() == slabs.grad(q).data_ptr()
+        oa.step(); ob_.step()
+    for (k, p), q in zip(ma.named_parameters(), mb.parameters()):
+        assert torch.allclose(p, q, rtol=1e-3, atol=2e-5), k
+    # state_dict is storage-agnostic and moments are AdamW-named views of the slabs
+    assert set(ma.state_dict()) == set(mb.state_dict())
+    st = ob_.state[mb.decoder.ln.weight]
+    assert st["exp_avg"].data_ptr() == slabs.span("M", mb.decoder.ln.weight, 1).data_ptr()
+    # gradient accumulation: a second backward without zero_grad doubles the slab (every kernel accumulates)
+    ob_.zero_grad()
+    mb(mel, ti, pm, targets=ty).backward()
+    single = slabs.G.clone()
+    mb(mel, ti, pm, targets=ty).backward()
+    assert float((slabs.G - 2 * single).norm() / (2 * single).norm()) < 1e-4

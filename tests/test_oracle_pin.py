@@ -86,12 +86,19 @@ def test_train_forward_matches_reference_golden(tiny_train, golden_dir):
 
 
 def test_train_bf16_autocast_matches_reference_golden(tiny_train, golden_dir):
+    """bf16 autocast on the CPU is host-dependent (oneDNN picks different bf16 kernels per CPU), so the golden bf16
+    samples of the generating host are a YARDSTICK, not a bit pattern: on any host the bf16 run must sit at the same
+    distance from the (host-independent) fp32 golden as the reference's own bf16 run did, and within twice that
+    noise of the recorded bf16 sample."""
     dims, sd, mel, ti, ty, pm = tiny_train
     g = torch.load(golden_dir / "model_tiny.pt", weights_only=False)
     with torch.no_grad():
         lb = OM.model_forward(sd, dims, mel, ti, pm, train_model=True, autocast_dtype=torch.bfloat16)
-    rel = (lb[:, ::16, ::997] - g["logits_bf16_sample"]).norm() / g["logits_bf16_sample"].norm()
-    assert float(rel) < 2e-3
+    rel = lambda a, b: float((a - b).norm() / b.norm())
+    noise = rel(g["logits_bf16_sample"], g["logits_fp32_sample"])      # the reference's own bf16 error (7.8e-3)
+    assert 0.5 * noise <= rel(lb[:, ::16, ::997], g["logits_fp32_sample"]) <= 1.5 * noise
+    assert rel(lb[:, ::16, ::997], g["logits_bf16_sample"]) <= 2.0 * noise
+    assert float(OM.token_ce(lb, ty)) == pytest.approx(g["loss_fp32"], rel=1e-3)
     assert float(OM.token_ce(lb, ty)) == pytest.approx(g["loss_bf16"], rel=1e-3)
 
 
@@ -127,6 +134,31 @@ def test_inference_model_and_kv_cache_match_reference_golden(golden_dir):
     # kv-cache steps == full re-forward (the invariant listed in SURVEY.md section 4)
     assert torch.allclose(steps[1][:, 0], full[:, 3], atol=2e-4)
     assert torch.allclose(steps[2][:, 0], full[:, 4], atol=2e-4)
+
+
+@pytest.mark.parametrize("name", ["base", "medium"])
+def test_width_goldens_pin_the_oracle_at_benchmark_widths(name, golden_dir):
+    """tests/golden/model_<variant>_2x2.pt: outputs of the unmodified reference at the benchmarked WIDTH (depth 2+2).  The
+    oracle must reproduce them before the GPU tests compare the CUDA path with the oracle at those widths."""
+    from dataclasses import replace
+
+    g = torch.load(golden_dir / f"model_{name}_2x2.pt", weights_only=False)
+    dims = replace(OM.variant_dims(name), n_audio_layer=2, n_text_layer=2)
+    sd = OM.init_state_dict(dims, seed=0, train=True)
+    for k, (s_, a_) in g["weight_checksums"].items():
+        assert float(sd[k].double().sum()) == pytest.approx(s_, rel=1e-9, abs=1e-9), k
+    mel = torch.from_numpy(logmel.log_mel_spectrogram(synth.waveforms(2).numpy()))
+    ti, ty, pm, _ = synth.text_batch(2)
+    p = {k: v.clone().requires_grad_(k != "encoder.positional_embedding") for k, v in sd.items()}
+    logits = OM.model_forward(p, dims, mel, ti, pm, train_model=True)
+    loss = OM.token_ce(logits, ty)
+    assert torch.allclose(logits.detach()[:, ::16, ::997], g["logits_fp32_sample"], atol=2e-4, rtol=1e-4)
+    assert float(loss) == pytest.approx(g["loss_fp32"], rel=1e-5)
+    loss.backward()
+    for k, n in g["grad_norms"].items():
+        assert float(p[k].grad.double().norm()) == pytest.approx(n, rel=2e-3, abs=1e-7), k
+    for k, smp in g["grad_samples"].items():
+        assert torch.allclose(p[k].grad.flatten()[::1013][:64], smp, atol=1e-6, rtol=2e-3), k
 
 
 @pytest.mark.skipif(not ref_import.available(), reason="reference tree not mounted (GPU box)")

@@ -125,7 +125,65 @@ def golden_grad_noise():
     print("grad_noise_tiny.pt")
 
 
+WIDTHS = {"base": (512, 8), "small": (768, 12), "medium": (1024, 16)}   # olmoasr/config/model_dims.py:28-89
+
+
+def golden_widths(depth=(2, 2)):
+    """The benchmarked variants at their real WIDTH and head count (what selects GEMM tile shapes, attention grids, LN
+    vector widths) but depth 2+2 so that the fp32 reference runs in seconds on a CPU.  From the UNMODIFIED reference:
+    fp32 loss, logits sample, per-tensor gradient norms and samples, weight checksums.  From the pinned oracle: the
+    reference's own bf16-autocast noise (logits rel-L2 and per-tensor gradient rel-L2 against fp32) -- the yardstick a
+    bf16 implementation is held to."""
+    from dataclasses import replace
+
+    ref_model, ref_inf, ref_dims = ref_import.load()
+    B = 2
+    mel = torch.from_numpy(logmel.log_mel_spectrogram(synth.waveforms(B).numpy()))
+    ti, ty, pm, _ = synth.text_batch(B)
+    for name in WIDTHS:
+        rd = replace(ref_dims.VARIANT_TO_DIMS[name], n_audio_layer=depth[0], n_text_layer=depth[1])
+        torch.manual_seed(0)
+        rm = ref_model.OLMoASR(rd)
+        logits = rm(mel, ti, pm)
+        loss = torch.nn.functional.cross_entropy(logits.view(-1, logits.shape[-1]), ty.view(-1), ignore_index=51864)
+        loss.backward()
+        gnorm = {k: float(p.grad.double().norm()) for k, p in rm.named_parameters()}
+        gsample = {k: p.grad.flatten()[::1013][:64].clone() for k, p in rm.named_parameters()
+                   if k.endswith(("conv1.weight", "blocks.0.attn.key.weight", "blocks.1.mlp.0.bias", "token_embedding.weight",
+                                  "decoder.positional_embedding", "blocks.1.cross_attn.query.weight", "decoder.ln.weight"))}
+        dims = replace(OM.variant_dims(name), n_audio_layer=depth[0], n_text_layer=depth[1])
+        sd = OM.init_state_dict(dims, 0, True)
+        assert all(torch.equal(sd[k], v) for k, v in rm.state_dict().items())
+
+        def grads(ac):
+            p = {k: v.clone().requires_grad_(k != "encoder.positional_embedding") for k, v in sd.items()}
+            lg = OM.model_forward(p, dims, mel, ti, pm, True, ac)
+            OM.token_ce(lg, ty).backward()
+            return lg.detach(), {k: v.grad for k, v in p.items() if v.grad is not None}
+
+        l32, g32 = grads(None)
+        lbf, gbf = grads(torch.bfloat16)
+        assert torch.equal(l32, logits.detach())
+        torch.save({
+            "variant": name, "depth": depth, "seed": 0, "batch": B,
+            "weight_checksums": checksums(rm.state_dict()),
+            "logits_fp32_sample": logits.detach()[:, ::16, ::997].clone(), "loss_fp32": float(loss),
+            "loss_bf16": float(OM.token_ce(lbf, ty)),
+            "logits_bf16_noise": float((lbf - l32).norm() / l32.norm()),
+            "grad_norms": gnorm, "grad_samples": gsample,
+            "grad_noise": {k: float((gbf[k] - g32[k]).norm() / g32[k].norm()) for k in g32},
+            "torch_version": torch.__version__,
+        }, OUT / f"model_{name}_{depth[0]}x{depth[1]}.pt")
+        print(f"model_{name}_{depth[0]}x{depth[1]}.pt loss", float(loss), "bf16 logits noise", float((lbf - l32).norm() / l32.norm()))
+
+
 if __name__ == "__main__":
-    golden_logmel()
-    golden_model()
-    golden_grad_noise()
+    which = sys.argv[1:] or ["logmel", "model", "grad_noise", "widths"]
+    if "logmel" in which:
+        golden_logmel()
+    if "model" in which:
+        golden_model()
+    if "grad_noise" in which:
+        golden_grad_noise()
+    if "widths" in which:
+        golden_widths()
