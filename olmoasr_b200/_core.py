@@ -199,6 +199,9 @@ def kv_len_from_padding_mask(padding_mask: Tensor) -> Tensor:
         return cached[1]
     if padding_mask.dim() != 3 or padding_mask.shape[1] != padding_mask.shape[2] or padding_mask.dtype != torch.float32:
         raise ValueError(f"padding_mask must be (B, n_ctx, n_ctx) float32, got {tuple(padding_mask.shape)} {padding_mask.dtype}")
+    if not padding_mask.is_cuda:
+        from ._lib import OasrError
+        raise OasrError("padding_mask must be a CUDA tensor (the key counts are derived on the device; no CPU fallback)")
     dev = padding_mask.device
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
     check_deferred_errors(dev)

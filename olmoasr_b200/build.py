@@ -52,6 +52,31 @@ def headers():
     return sorted(CSRC.glob("*.cuh")) + [CSRC.parent.parent / "include" / "oasr_b200.h"]
 
 
+def build_variant(name: str, defines) -> Path:
+    """A/B build: the whole library compiled with extra -D flags into csrc/_ab/<name>.so (select it at run time with
+    OASR_B200_LIB; the default library is untouched)."""
+    out_dir = CSRC / "_ab"
+    obj_dir = out_dir / ("_obj_" + name)
+    obj_dir.mkdir(parents=True, exist_ok=True)
+    nvcc = _nvcc()
+
+    def one(src: Path):
+        obj = obj_dir / (src.stem + ".o")
+        r = subprocess.run([nvcc, *NVCC_FLAGS, *defines, "-c", str(src), "-o", str(obj)], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src.name}:\n{r.stdout}\n{r.stderr}")
+        return str(obj)
+
+    with cf.ThreadPoolExecutor(max_workers=8) as ex:
+        objs = list(ex.map(one, sources()))
+    lib = out_dir / f"{name}.so"
+    r = subprocess.run([nvcc, "-shared", "-o", str(lib), *objs], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    shutil.rmtree(obj_dir, ignore_errors=True)
+    return lib
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
     srcs = sources()
     stamp = OBJ_DIR / "stamp.txt"
@@ -92,5 +117,9 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
 
 if __name__ == "__main__":
-    out = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
-    print(out)
+    if "--variant" in sys.argv:     # python -m olmoasr_b200.build --variant attn_poly2 -DOASR_ATTN_POLY=2
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], [a for a in sys.argv[i + 2:] if a.startswith("-D")]))
+    else:
+        out = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+        print(out)

@@ -41,6 +41,11 @@ constexpr int TMEM_COLS = 512;
 constexpr int S_COL = 0, O_COL = 256;        // + t*128 / + t*64
 constexpr float RESCALE_LOG2 = 8.0f;
 constexpr int SOFTMAX_REGS = 224, CONTROL_REGS = 56;   // 8 * SOFTMAX + 4 * CONTROL == 12 * 168
+// Share of the exponentials of an unmasked tile evaluated on the FMA pipe (exp2_poly2) instead of MUFU.EX2:
+// 0 = none, 1 = every fourth pair (25 %), 2 = every second pair (50 %).  A/B builds: python -m olmoasr_b200.build --variant.
+#ifndef OASR_ATTN_POLY
+#define OASR_ATTN_POLY 0
+#endif
 
 struct AttnParams {
   bf16* o;
@@ -278,7 +283,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       // POLY: odd pairs go through the FMA-pipe polynomial, even pairs through MUFU.EX2 (the two pipes run side by
       // side).  Masked tiles keep MUFU for every element so that -inf maps to exactly 0.
       auto emit_p = [&](auto poly_tag) {
-        constexpr bool POLY = decltype(poly_tag)::value;
+        constexpr int POLY = decltype(poly_tag)::value;
 #pragma unroll
         for (int cc = 0; cc < BKV / 32; ++cc) {
           const uint32_t half_base = sPt + (cc >> 1) * (P_BYTES / 2) + r * 128;
@@ -290,7 +295,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
               const int i = cc * 32 + q4 * 8 + e * 2;
               const float2 x = __ffma2_rn(make_float2(v[i], v[i + 1]), c2, n2);
               float2 pe;
-              if (POLY && (e & 1)) pe = exp2_poly2(x);
+              if ((POLY == 2 && (e & 1)) || (POLY == 1 && e == 3)) pe = exp2_poly2(x);
               else pe = make_float2(fast_exp2(x.x), fast_exp2(x.y));
               sums[e] = __fadd2_rn(sums[e], pe);
               w[e] = pack_bf16x2(pe.x, pe.y);
@@ -302,9 +307,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           }
         }
       };
-      // ncu (profiles/r01_ncu_kernel_metrics.txt): XU pipe 30 %, issue slots 50 % busy with two softmax warps per
-      // scheduler -- issue slots, not MUFU, are scarce, so the polynomial path (6 slots per element) stays off
-      emit_p(std::false_type{});
+      // ncu of the MUFU-only build (profiles/r01_ncu_kernel_metrics.txt): XU pipe 59.5 %, issue slots 36.7 %, tensor
+      // pipe 29.7 % -- 128 x 128 ex2 per tile at 16 / clk / SM is twice the tile's MMA time, so a share of the
+      // exponentials moves to the FMA pipe (OASR_ATTN_POLY; measured per build in profiles/r02_attention_poly_ab.txt)
+      if (OASR_ATTN_POLY != 0 && limit >= BKV) emit_p(std::integral_constant<int, OASR_ATTN_POLY>{});
+      else emit_p(std::integral_constant<int, 0>{});
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
       __syncwarp();

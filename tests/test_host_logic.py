@@ -53,19 +53,20 @@ def test_tile_heuristics():
     assert _core._pick_split_k(1624, 224) == 1
 
 
-def test_kv_len_from_padding_mask():
+def test_kv_len_accepts_lengths_and_rejects_what_it_cannot_derive():
+    """Key counts are derived from the dense mask by a CUDA kernel (tests/test_kernels_gpu.py); on the host only the
+    argument contract is visible: integer lengths pass through, malformed masks and CPU masks raise."""
+    from olmoasr_b200._lib import OasrError
+
     _, _, pm, lens = synthetic.text_batch(5)
-    assert torch.equal(_core.kv_len_from_padding_mask(pm).long(), lens)
-
-
-def test_kv_len_is_cached_per_mask_object_and_invalidated_by_in_place_edits():
-    _, _, pm, lens = synthetic.text_batch(3)
-    a = _core.kv_len_from_padding_mask(pm)
-    assert _core.kv_len_from_padding_mask(pm) is a            # 24 decoder blocks share one computation
-    pm[0, :, 5:] = -float("inf")                               # in-place edit bumps the version counter
-    b = _core.kv_len_from_padding_mask(pm)
-    assert b is not a and int(b[0]) == 5 and torch.equal(b[1:].long(), lens[1:])
-    assert torch.equal(_core.kv_len_from_padding_mask(pm.clone()).long(), b.long())   # a new tensor recomputes
+    assert torch.equal(_core.kv_len_from_padding_mask(lens), lens.int())
+    assert _core.kv_len_from_padding_mask(lens.int()).dtype == torch.int32
+    with pytest.raises(ValueError, match="padding_mask must be"):
+        _core.kv_len_from_padding_mask(pm[:, :10])             # not square
+    with pytest.raises(ValueError, match="padding_mask must be"):
+        _core.kv_len_from_padding_mask(pm.double())
+    with pytest.raises(OasrError, match="CUDA"):
+        _core.kv_len_from_padding_mask(pm)                     # no CPU path
 
 
 def test_side_stream_helper_is_inert_off_cuda():
@@ -234,3 +235,140 @@ def test_blockwise_grad_reducer_matches_ddp_averaging_world2_gloo(tmp_path, coal
             per_rank.append([p.grad.clone() for p in net.parameters() if p.grad is not None])
         for got, g0, g1 in zip(r["grads"][it], per_rank[0], per_rank[1]):
             assert torch.allclose(got, (g0 + g1) / 2, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------- parameter slabs (host logic)
+def _small_dims():
+    from olmoasr_b200.config.model_dims import ModelDimensions
+    return ModelDimensions(80, 1500, 64, 1, 2, 51864, 448, 64, 1, 2)
+
+
+def test_slab_layout_keeps_the_state_dict_and_gives_fused_views():
+    from olmoasr_b200.model import OLMoASR
+
+    torch.manual_seed(0)
+    m = OLMoASR(_small_dims())
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    n_params = sum(p.numel() for p in m.parameters())
+    sl = m.use_slabs()
+    after = m.state_dict()
+    assert list(after) == list(before) and all(torch.equal(after[k], before[k]) for k in before)   # names, order, values
+    assert n_params <= sl.numel <= n_params + 64 * 64                     # only the zero gaps of the bias-less key projections
+    assert all(p.data_ptr() == sl.P.data_ptr() + 4 * sl.offset[id(p)] for p in m.parameters())
+    assert all(p.grad.data_ptr() == sl.G.data_ptr() + 4 * sl.offset[id(p)] for p in m.parameters())
+    for blk in list(m.encoder.blocks) + list(m.decoder.blocks):
+        for a in (blk.attn, blk.cross_attn):
+            if a is None:
+                continue
+            w, b = a.fused_qkv()
+            d = a.query.weight.shape[0]
+            assert w.shape == (3 * d, d) and w.dtype == torch.bfloat16 and b.shape == (3 * d,) and b.dtype == torch.float32
+            assert torch.equal(b[:d], a.query.bias) and torch.equal(b[2 * d:], a.value.bias) and float(b[d:2 * d].abs().max()) == 0
+            assert w.data_ptr() == sl.S.data_ptr() + 2 * sl.offset[id(a.query.weight)]
+            wk, bk = a.fused_kv()
+            assert wk.shape == (2 * d, d) and wk.data_ptr() == sl.S.data_ptr() + 2 * sl.offset[id(a.key.weight)]
+    # layout order == backward completion order: decoder first, conv stem last
+    assert sl.offset[id(m.decoder.ln.weight)] == 0
+    assert sl.offset[id(m.encoder.conv1.bias)] == max(sl.offset.values())
+    assert sl.offset[id(m.decoder.blocks[1].mlp_ln.weight)] < sl.offset[id(m.decoder.blocks[0].mlp_ln.weight)]
+    # load_state_dict writes through the views and bumps the versions the shadow sync keys on
+    sig = sl._signature()
+    m.load_state_dict({k: v + 1.0 if v.is_floating_point() else v for k, v in before.items()})
+    assert sl._signature() != sig and torch.equal(sl.span("P", m.decoder.ln.weight, 64), before["decoder.ln.weight"] + 1.0)
+    # zero_grad is one memset and re-attaches dropped views
+    m.decoder.ln.weight.grad = None
+    sl.G.fill_(3.0)
+    sl.zero_grad()
+    assert float(sl.G.abs().max()) == 0 and m.decoder.ln.weight.grad.data_ptr() == sl.G.data_ptr()
+    # grad_units partition the layout in order (what SlabGradSync cuts into all-reduce segments)
+    order = {pid: i for i, pid in enumerate(sl.layout_order)}
+    nxt = 0
+    for ps, mod in m.grad_units():
+        idx = sorted(order[id(p)] for p in ps)
+        assert idx == list(range(nxt, nxt + len(ps)))
+        nxt += len(ps)
+    assert nxt == len(order)
+    with pytest.raises(ValueError, match="every trainable parameter"):
+        from olmoasr_b200.slab import ParamSlabs
+        ParamSlabs(torch.nn.Linear(4, 4), layout=[])
+
+
+class _ToySlabModel(torch.nn.Module):
+    """Two 'blocks' + a head with the grad_units / _bwd_done_cb protocol of OLMoASRBase (host logic only)."""
+
+    def __init__(self):
+        super().__init__()
+        self.b0, self.b1, self.head = torch.nn.Linear(64, 64), torch.nn.Linear(64, 64), torch.nn.Linear(64, 64)
+        for mod in (self.b0, self.b1, self.head):
+            mod._bwd_done_cb = None
+
+    def forward(self, x):
+        return self.head(torch.tanh(self.b1(torch.tanh(self.b0(x)))))
+
+    def grad_units(self):   # backward order: head, b1, b0
+        return [(list(self.head.parameters()), self.head), (list(self.b1.parameters()), self.b1), (list(self.b0.parameters()), self.b0)]
+
+
+def _slab_sync_worker(rank, world, port, out):
+    from olmoasr_b200.ddp import SlabGradSync
+    from olmoasr_b200.slab import ParamSlabs
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(rank)                       # different initial weights: the constructor must broadcast rank 0's
+    net = _ToySlabModel()
+    layout = [p for ps, _ in net.grad_units() for p in ps]
+    slabs = ParamSlabs(net, layout, shadows=False)
+    sync = SlabGradSync(net, slabs, bucket_bytes=1)      # every unit its own segment
+    assert len(sync.segments) == 3 and sync.segments[0][0] == 0 and sync.segments[-1][1] == slabs.numel
+    assert all(a[1] == b[0] for a, b in zip(sync.segments, sync.segments[1:]))
+    launched_early = []
+    results = []
+    for it in range(3):
+        slabs.zero_grad()
+        x = torch.randn(5, 64, generator=torch.Generator().manual_seed(100 * it + rank))
+        loss = net(x).pow(2).mean()
+        if it == 2:                                # gradient accumulation: first micro-batch inside no_sync()
+            with sync.no_sync():
+                loss.backward()
+                for mod in (net.head, net.b1, net.b0):
+                    mod._bwd_done_cb()
+                assert not sync._works
+            x = torch.randn(5, 64, generator=torch.Generator().manual_seed(999 + rank))
+            loss = net(x).pow(2).mean()
+        loss.backward()                            # autograd accumulates into the slab views
+        for mod in (net.head, net.b1):             # the fused backward fires these as it goes; b0's never fires here
+            mod._bwd_done_cb()
+        launched_early.append(list(sync._launched))
+        inv = sync.finish()                        # launches the segment nobody triggered, waits, re-arms
+        results.append((slabs.G * inv).clone())
+    if rank == 0:
+        torch.save({"grads": results, "weights": slabs.P.clone(), "early": launched_early, "offsets": [slabs.offset[id(p)] for p in layout]}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_slab_grad_sync_matches_ddp_averaging_world2_gloo(tmp_path):
+    out = str(tmp_path / "r0.pt")
+    mp.spawn(_slab_sync_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    r = torch.load(out, weights_only=False)
+    assert r["early"][0] == [True, True, False]
+    torch.manual_seed(0)
+    net = _ToySlabModel()
+    layout = [p for ps, _ in net.grad_units() for p in ps]
+    flat_w = torch.cat([p.detach().reshape(-1) for p in layout])
+    assert torch.equal(r["weights"][: flat_w.numel()], flat_w)          # rank 0's weights everywhere (sizes are 64-multiples: no gaps)
+
+    def per_rank_grads(seed_fn):
+        gs = []
+        for rank in range(2):
+            net.zero_grad(set_to_none=True)
+            for seed in seed_fn(rank):
+                x = torch.randn(5, 64, generator=torch.Generator().manual_seed(seed))
+                net(x).pow(2).mean().backward()
+            gs.append(torch.cat([p.grad.reshape(-1) for p in layout]))
+        return (gs[0] + gs[1]) / 2
+
+    for it in range(2):
+        assert torch.allclose(r["grads"][it], per_rank_grads(lambda rank: [100 * it + rank]), atol=1e-6)
+    assert torch.allclose(r["grads"][2], per_rank_grads(lambda rank: [200 + rank, 999 + rank]), atol=1e-6)   # accumulated, synced once

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--gemm-table", action="store_true", help="per-shape GEMM time / TFLOP/s (CUDA events per launch)")
     ap.add_argument("--serial", action="store_true", help="side stream off: per-kernel device times do not overlap")
     ap.add_argument("--no-profiler", action="store_true", help="just run the steps (when wrapped in ncu)")
+    ap.add_argument("--no-slabs", action="store_true", help="plain parameter storage + pointer-table optimizer")
     args = ap.parse_args()
     import olmoasr_b200 as ob
     from olmoasr_b200 import synthetic as synth
@@ -37,7 +38,8 @@ def main():
         dims = replace(dims, n_audio_layer=args.layers, n_text_layer=args.layers)
     with torch.device(dev):
         model = OLMoASR(dims)
-    opt = FusedAdamW(model.parameters())
+    slabs = None if args.no_slabs else model.use_slabs()
+    opt = FusedAdamW(model.parameters(), slabs=slabs)
     B = args.batch
     wav = synth.waveforms(B, int16=True).to(dev)
     ti, ty, pm, _ = (t.to(dev) for t in synth.text_batch(B))
@@ -45,7 +47,7 @@ def main():
     def step():
         mel = ob.log_mel_spectrogram(wav)
         loss = model(mel, ti, pm, targets=ty)
-        opt.zero_grad(set_to_none=True)
+        opt.zero_grad()
         loss.backward()
         opt.step()
         return loss
