@@ -177,6 +177,68 @@ OASR_API int oasr_adamw_flat(float* p, const float* g, float* m, float* v, void*
                              const float* state, float lr, float beta1, float beta2, float eps, float weight_decay,
                              void* stream);
 
+/* ---- greedy kv-cache decode step (BASELINE.json config 5) -------------------------------------------------
+ * The per-step kernels behind `model.decode(mel, DecodingOptions(language="en", without_timestamps=True))`
+ * (scripts/eval/eval.py:1846-1847 -> third-party whisper.decoding -> olmoasr/inf_model.py:320-362 TextDecoder.forward,
+ * :150-196 MultiHeadAttention, :422-453 kv-cache hooks).  Activation dtype T = fp16 (upstream default fp16=True) or
+ * bf16; every rounding point of inf_model.py:172-196 is reproduced (see csrc/decode.cu).  All per-step state (position,
+ * tokens, finished flags) is in device memory so that one CUDA graph of these launches is replayed for every step.
+ * Argument blocks are plain host structs passed by pointer (read during the call only). */
+#define OASR_DTYPE_BF16 0
+#define OASR_DTYPE_F16 1
+#define OASR_DTYPE_F32 2
+
+/* x = T(token_embedding[tokens[n, *pos]] + positional_embedding[*pos])   (inf_model.py:334-338) */
+OASR_API int oasr_dec_embed(const int32_t* tokens, int64_t ld_tokens, const int32_t* pos_ptr, const float* emb,
+                            const float* pos_emb, void* x, int64_t n_seq, int64_t d, int64_t n_vocab, int dtype,
+                            void* stream);
+
+/* Skinny Linear for <= 64 sequences: out = epilogue(prologue(x) W^T + bias), W (N, K) in dtype T streamed once.
+ *   x_mode 0: x (M, K) T;  1: LayerNorm(x; gamma, beta, eps) fused (inf_model.py LayerNorm: fp32, one rounding);
+ *          2: x = round_T(sum of n_partials fp32 slabs (each partial_stride elements apart))  -- dec_attention's output
+ *   epi    0: T(acc + bias_T)   1: T(gelu_erf(T(acc + bias_T)))   2: T(res + T(acc + bias_T))
+ *          3: float(T(acc)) into fp32 `out` (tied logits, inf_model.py:357-360)
+ *          4: N = 3d fused [q | k | v]: q -> out, k / v -> row *pos of the static caches (n_seq, cache_len, d)
+ *             (replaces the torch.cat of the kv-cache hook, inf_model.py:439-445) */
+typedef struct oasr_dec_linear_args {
+  const void* x; int64_t ldx; int32_t x_mode; int32_t n_partials; int64_t partial_stride;
+  const float* ln_gamma; const float* ln_beta; float ln_eps; int32_t epi;
+  const void* W; const float* bias;
+  void* out; int64_t ldo; const void* res; int64_t ldres;
+  void* k_cache; void* v_cache; int64_t cache_len; const int32_t* pos_ptr;
+  int32_t M; int32_t N; int32_t K; int32_t dtype;
+} oasr_dec_linear_args;
+OASR_API int oasr_dec_linear(const oasr_dec_linear_args* args, void* stream);
+
+/* Single-query attention over a static cache (inf_model.py:172-196 with n_ctx == 1): keys [0, *pos] (self) or
+ * [0, n_keys) (cross); k / v element (n, j, h*64 + c) at n * kv_seq_stride + j * kv_row_stride + h*64 + c.
+ * scores: (n_seq, n_head, scores_ld) f32 scratch; out_partial: (n_splits, n_seq, ld_out) f32, summed and rounded by
+ * the consumer (oasr_dec_linear x_mode 2).  Head dim 64. */
+typedef struct oasr_dec_attn_args {
+  const void* q; int64_t ldq;
+  const void* k; const void* v; int64_t kv_seq_stride; int64_t kv_row_stride;
+  float* scores; int64_t scores_ld;
+  float* out_partial; int64_t ld_out;
+  const int32_t* pos_ptr; int32_t n_keys;
+  int32_t n_seq; int32_t n_head; int32_t n_splits; float scale; int32_t dtype;
+} oasr_dec_attn_args;
+OASR_API int oasr_dec_attention(const oasr_dec_attn_args* args, void* stream);
+
+/* Logit filters + greedy choice + bookkeeping (whisper/decoding.py SuppressBlank, SuppressTokens, GreedyDecoder.update,
+ * the no-speech probability and the stop test of DecodingTask._main_loop), then *pos += 1.
+ * tokens: (n_seq, ld_tokens) int32, position *pos holds the token just fed; the choice is written to *pos + 1 once
+ * *pos >= sample_begin - 1.  done_flag[0] = 1 when every sequence's newest token is eot. */
+typedef struct oasr_dec_sample_args {
+  const float* logits; int64_t ld_logits; int32_t* tokens; int64_t ld_tokens; int32_t* pos_ptr;
+  const uint8_t* suppress; float* sum_logprobs; float* no_speech_prob; int32_t* n_unfinished; int32_t* done_flag;
+  int32_t n_seq; int32_t n_vocab; int32_t sample_begin; int32_t sot_index; int32_t suppress_blank; int32_t blank;
+  int32_t eot; int32_t no_speech;
+} oasr_dec_sample_args;
+OASR_API int oasr_dec_sample(const oasr_dec_sample_args* args, void* stream);
+
+/* elementwise dtype conversion (weights fp32 -> T once per engine; bf16 encoder output / cross K,V -> fp16) */
+OASR_API int oasr_convert(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -975,22 +975,51 @@ class OLMoASRBase(nn.Module):
         return self.dims.n_vocab - 51765 - int(self.is_multilingual)
 
     def install_kv_cache_hooks(self, cache: Optional[dict] = None):
-        """Same contract as the reference (model.py:925-964): forward hooks on every decoder key / value Linear,
-        keyed by module identity; outputs longer than n_text_ctx (cross-attention) are stored once."""
-        cache = {**cache} if cache is not None else {}
+        """The reference's kv-cache protocol (model.py:925-964 / inf_model.py:422-453), kept for third-party loops
+        (whisper.decoding.PyTorchInference) and for this package's sampling / timestamp-rule paths: forward hooks on every
+        decoder key / value Linear, a dict keyed by module identity, cross-attention outputs (longer than n_text_ctx) stored
+        once.  Unlike the reference there is no torch.cat per step: each self-attention projection owns one pre-allocated
+        (B, n_text_ctx, d) buffer, new rows are written behind the cached ones and the dict entry is a growing VIEW of it.
+        (The greedy fast path does not come through here at all: olmoasr_b200/decode_engine.py.)"""
+        store = _KVCacheStore(self.dims.n_text_ctx, dict(cache) if cache is not None else {})
         hooks = []
+        for blk in self.decoder.blocks:
+            for att in (blk.attn, blk.cross_attn):
+                if att is not None:
+                    hooks.append(att.key.register_forward_hook(store.on_projection))
+                    hooks.append(att.value.register_forward_hook(store.on_projection))
+        return store.cache, hooks
 
-        def save_to_cache(module, _, output):
-            if module not in cache or output.shape[1] > self.dims.n_text_ctx:
-                cache[module] = output
-            else:
-                cache[module] = torch.cat([cache[module], output], dim=1).detach()
-            return cache[module]
+    def decode_engine(self, dtype: torch.dtype = torch.float16, max_batch: int = 64):
+        """The device-resident greedy decoder for this model (one per activation dtype, built on first use)."""
+        from .decode_engine import DecodeEngine
 
-        def install_hooks(layer: nn.Module):
-            if isinstance(layer, MultiHeadAttention):
-                hooks.append(layer.key.register_forward_hook(save_to_cache))
-                hooks.append(layer.value.register_forward_hook(save_to_cache))
+        engines = self.__dict__.setdefault("_engines", {})
+        key = (dtype, max_batch)
+        if key not in engines:
+            engines[key] = DecodeEngine(self, dtype, max_batch)
+        return engines[key]
 
-        self.decoder.apply(install_hooks)
-        return cache, hooks
+
+class _KVCacheStore:
+    """Backing storage of `install_kv_cache_hooks`: module -> (buffer, rows in use)."""
+
+    def __init__(self, n_text_ctx: int, cache: dict):
+        self.n_text_ctx = n_text_ctx
+        self.cache = cache
+        self.buffers: Dict[nn.Module, Tensor] = {}
+
+    def on_projection(self, module, _inputs, output: Tensor):
+        rows = output.shape[1]
+        if rows > self.n_text_ctx:                     # cross-attention keys / values of the 1500 audio frames: computed once
+            self.cache[module] = output
+            return output
+        buf = self.buffers.get(module)
+        used = self.cache[module].shape[1] if (buf is not None and module in self.cache) else 0
+        if buf is None or buf.shape[0] != output.shape[0] or buf.dtype != output.dtype or used + rows > buf.shape[1]:
+            buf = torch.empty((output.shape[0], max(self.n_text_ctx, rows), output.shape[2]), device=output.device, dtype=output.dtype)
+            self.buffers[module] = buf
+            used = 0
+        buf[:, used:used + rows] = output.detach()
+        self.cache[module] = buf[:, :used + rows]
+        return self.cache[module]

@@ -26,6 +26,37 @@ class OasrError(RuntimeError):
     pass
 
 
+c_i32 = ctypes.c_int32
+c_float_p = ctypes.c_void_p
+DTYPE_BF16, DTYPE_F16, DTYPE_F32 = 0, 1, 2
+
+
+class DecLinearArgs(ctypes.Structure):  # oasr_dec_linear_args (include/oasr_b200.h)
+    _fields_ = [("x", c_void_p), ("ldx", c_i64), ("x_mode", c_i32), ("n_partials", c_i32), ("partial_stride", c_i64),
+                ("ln_gamma", c_void_p), ("ln_beta", c_void_p), ("ln_eps", c_float), ("epi", c_i32),
+                ("W", c_void_p), ("bias", c_void_p),
+                ("out", c_void_p), ("ldo", c_i64), ("res", c_void_p), ("ldres", c_i64),
+                ("k_cache", c_void_p), ("v_cache", c_void_p), ("cache_len", c_i64), ("pos_ptr", c_void_p),
+                ("M", c_i32), ("N", c_i32), ("K", c_i32), ("dtype", c_i32)]
+
+
+class DecAttnArgs(ctypes.Structure):  # oasr_dec_attn_args
+    _fields_ = [("q", c_void_p), ("ldq", c_i64),
+                ("k", c_void_p), ("v", c_void_p), ("kv_seq_stride", c_i64), ("kv_row_stride", c_i64),
+                ("scores", c_void_p), ("scores_ld", c_i64),
+                ("out_partial", c_void_p), ("ld_out", c_i64),
+                ("pos_ptr", c_void_p), ("n_keys", c_i32),
+                ("n_seq", c_i32), ("n_head", c_i32), ("n_splits", c_i32), ("scale", c_float), ("dtype", c_i32)]
+
+
+class DecSampleArgs(ctypes.Structure):  # oasr_dec_sample_args
+    _fields_ = [("logits", c_void_p), ("ld_logits", c_i64), ("tokens", c_void_p), ("ld_tokens", c_i64), ("pos_ptr", c_void_p),
+                ("suppress", c_void_p), ("sum_logprobs", c_void_p), ("no_speech_prob", c_void_p), ("n_unfinished", c_void_p),
+                ("done_flag", c_void_p),
+                ("n_seq", c_i32), ("n_vocab", c_i32), ("sample_begin", c_i32), ("sot_index", c_i32), ("suppress_blank", c_i32),
+                ("blank", c_i32), ("eot", c_i32), ("no_speech", c_i32)]
+
+
 # name -> argtypes (restype is always int unless listed in _RESTYPES)
 _SIGNATURES = {
     "oasr_abi_version": [],
@@ -64,6 +95,11 @@ _SIGNATURES = {
     "oasr_adamw_step": [c_void_p, c_void_p, c_i64, c_void_p, c_float, c_float, c_float, c_float, c_float, c_void_p],
     "oasr_adamw_flat": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_float, c_float, c_float,
                         c_float, c_float, c_void_p],
+    "oasr_dec_embed": [c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_int, c_void_p],
+    "oasr_dec_linear": [ctypes.POINTER(DecLinearArgs), c_void_p],
+    "oasr_dec_attention": [ctypes.POINTER(DecAttnArgs), c_void_p],
+    "oasr_dec_sample": [ctypes.POINTER(DecSampleArgs), c_void_p],
+    "oasr_convert": [c_void_p, c_int, c_void_p, c_int, c_i64, c_void_p],
     "oasr_gemm_bf16": [c_void_p, c_i64, c_int, c_void_p, c_i64, c_int, c_void_p, c_i64, c_void_p, c_void_p,
                        c_void_p, c_i64, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_void_p],
 }
@@ -125,7 +161,7 @@ def stream():
 
 
 # kernels launched per entry point (memsets not counted) -- bench.py reports the total as `gpu_launches`
-_LAUNCHES_PER_CALL = {"oasr_logmel": 3, "oasr_attention_bwd": 3}
+_LAUNCHES_PER_CALL = {"oasr_logmel": 3, "oasr_attention_bwd": 3, "oasr_dec_attention": 2, "oasr_dec_sample": 2}
 LAUNCH_COUNT = 0
 
 

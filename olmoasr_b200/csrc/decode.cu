@@ -1,0 +1,527 @@
+// Greedy kv-cache decode step (BASELINE.json config 5) as a fixed sequence of HBM-bound kernels that a CUDA graph replays:
+// every piece of per-step state (current position, token ids, finished flags) lives on the device.
+//
+// Replaces, per step and per decoder layer, what the reference does through stock modules
+// (olmoasr/inf_model.py:320-362 TextDecoder.forward, :150-196 MultiHeadAttention, :422-453 kv-cache hooks) and the
+// third-party greedy loop (whisper/decoding.py: PyTorchInference.logits, SuppressBlank / SuppressTokens,
+// GreedyDecoder.update) that drives it from `model.decode` (scripts/eval/eval.py:1846-1847).
+//
+// The reference's decode step is bound by weight and KV-cache reads (small: 277.8 MB of fp16 weights per step shared by
+// all sequences, 55.3 MB of cross-attention K/V per sequence per step), plus a host-built mask, per-call fp32->fp16 weight
+// casts and 2 L torch.cat reallocations.  Here:
+//   * weights are cast once into the activation dtype (fp16 = upstream default `fp16=True`, or bf16);
+//   * dec_linear: a skinny GEMM (<= 64 sequences) that streams each weight row exactly once with 16-byte loads and
+//     feeds mma.sync.m16n8k16 (fp32 accumulate); the preceding LayerNorm, the bias, GELU, the residual add and the
+//     scatter of new K/V rows into the pre-allocated cache are all fused into it -- 6 of the 10 launches per layer;
+//   * dec_attn_scores / dec_attn_pv: single-query attention that reads every cached K and V element once (16-byte
+//     loads, 8 lanes per key row), key ranges split over CTAs when batch x heads cannot fill 148 SMs;
+//   * dec_sample: logit filters + argmax + log-prob + eot bookkeeping in one pass over the fp32 logits.
+//
+// Rounding points are the reference's in the activation dtype T (inf_model.py:172-196): q*hd^-0.25 and k*hd^-0.25 rounded
+// to T, q.k accumulated in fp32 and rounded to T, softmax in fp32, probabilities rounded to T, p.v accumulated in fp32 and
+// rounded once; every Linear output is round_T(acc + bias_T); LayerNorm is computed in fp32 and rounded once;
+// residuals are round_T(x + y); logits are float(round_T(x . E^T)).
+#include "common.cuh"
+
+#include <cuda_fp16.h>
+
+namespace oasr {
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------- dtype traits
+template <typename T> struct DT;
+template <> struct DT<__half> {
+  static __device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
+  static __device__ __forceinline__ __half from_f(float v) { return __float2half_rn(v); }
+  static __device__ __forceinline__ float2 unpack2(uint32_t u) {
+    return __half22float2(*reinterpret_cast<const __half2*>(&u));
+  }
+  static __device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  static __device__ __forceinline__ void mma(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                             uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  }
+};
+template <> struct DT<bf16> {
+  static __device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+  static __device__ __forceinline__ bf16 from_f(float v) { return __float2bfloat16_rn(v); }
+  static __device__ __forceinline__ float2 unpack2(uint32_t u) { return unpack_bf16x2(u); }
+  static __device__ __forceinline__ uint32_t pack2(float a, float b) { return pack_bf16x2(a, b); }
+  static __device__ __forceinline__ void mma(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                             uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  }
+};
+template <typename T> __device__ __forceinline__ float rnd(float v) { return DT<T>::to_f(DT<T>::from_f(v)); }
+
+__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// ---------------------------------------------------------------------------------------------------------- embedding
+// x[n] = T(token_embedding[tokens[n, pos]] + positional_embedding[pos])   (inf_model.py:334-338; fp32 add, one rounding)
+template <typename T>
+__global__ void dec_embed_kernel(const int32_t* __restrict__ tokens, int64_t ld_tokens, const int32_t* __restrict__ pos_ptr,
+                                 const float* __restrict__ emb, const float* __restrict__ pos_emb, T* __restrict__ x, int d,
+                                 int n_vocab) {
+  const int n = blockIdx.x;
+  const int pos = *pos_ptr;
+  int tok = tokens[n * ld_tokens + pos];
+  if (tok < 0 || tok >= n_vocab) tok = 0;
+  const float* e = emb + static_cast<int64_t>(tok) * d;
+  const float* p = pos_emb + static_cast<int64_t>(pos) * d;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) x[static_cast<int64_t>(n) * d + c] = DT<T>::from_f(e[c] + p[c]);
+}
+
+// ---------------------------------------------------------------------------------------------------------- skinny GEMM
+enum { X_PLAIN = 0, X_LAYERNORM = 1, X_PARTIAL_SUM = 2 };
+enum { EPI_STORE = 0, EPI_GELU = 1, EPI_RESIDUAL = 2, EPI_LOGITS_F32 = 3, EPI_QKV_SCATTER = 4 };
+
+template <typename T>
+__device__ __forceinline__ uint4 load_x8(const oasr_dec_linear_args& a, const float (*s_stat)[2], int row, int k) {
+  if (row >= a.M) return make_uint4(0, 0, 0, 0);
+  if (a.x_mode == X_PARTIAL_SUM) {   // sum of S fp32 partial outputs of dec_attn_pv, rounded once (the `w @ v` output)
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float* p = static_cast<const float*>(a.x) + static_cast<int64_t>(row) * a.K + k;
+    for (int s = 0; s < a.n_partials; ++s) {
+      const float4 lo = *reinterpret_cast<const float4*>(p + static_cast<int64_t>(s) * a.partial_stride);
+      const float4 hi = *reinterpret_cast<const float4*>(p + static_cast<int64_t>(s) * a.partial_stride + 4);
+      v[0] += lo.x; v[1] += lo.y; v[2] += lo.z; v[3] += lo.w; v[4] += hi.x; v[5] += hi.y; v[6] += hi.z; v[7] += hi.w;
+    }
+    return make_uint4(DT<T>::pack2(v[0], v[1]), DT<T>::pack2(v[2], v[3]), DT<T>::pack2(v[4], v[5]), DT<T>::pack2(v[6], v[7]));
+  }
+  const uint4 u = *reinterpret_cast<const uint4*>(static_cast<const T*>(a.x) + static_cast<int64_t>(row) * a.ldx + k);
+  if (a.x_mode == X_PLAIN) return u;
+  // LayerNorm on the fly: fp32 statistics of the whole row (s_stat), affine, one rounding to T (inf_model.py LayerNorm)
+  const float mean = s_stat[row][0], rstd = s_stat[row][1];
+  const float4 g0 = *reinterpret_cast<const float4*>(a.ln_gamma + k), g1 = *reinterpret_cast<const float4*>(a.ln_gamma + k + 4);
+  const float4 b0 = *reinterpret_cast<const float4*>(a.ln_beta + k), b1 = *reinterpret_cast<const float4*>(a.ln_beta + k + 4);
+  const float2 x0 = DT<T>::unpack2(u.x), x1 = DT<T>::unpack2(u.y), x2 = DT<T>::unpack2(u.z), x3 = DT<T>::unpack2(u.w);
+  return make_uint4(DT<T>::pack2((x0.x - mean) * rstd * g0.x + b0.x, (x0.y - mean) * rstd * g0.y + b0.y),
+                    DT<T>::pack2((x1.x - mean) * rstd * g0.z + b0.z, (x1.y - mean) * rstd * g0.w + b0.w),
+                    DT<T>::pack2((x2.x - mean) * rstd * g1.x + b1.x, (x2.y - mean) * rstd * g1.y + b1.y),
+                    DT<T>::pack2((x3.x - mean) * rstd * g1.z + b1.z, (x3.y - mean) * rstd * g1.w + b1.w));
+}
+
+// y[m, n] = epilogue( sum_k x[m, k] W[n, k] ),  M <= 16 MT rows, one CTA = 16 output columns, 8 warps split K.
+// Thread (g = lane / 4, t = lane % 4) loads 16 contiguous bytes of W row n0 + 8 j + g at k0 + 8 t (a warp touches 8 rows x
+// 64 B: whole sectors) and the SAME 8 k positions of x rows g, g + 8 of every 16-row tile: the two m16n8k16 MMAs per
+// 32-wide k step then use a permuted k order that A and B agree on, so no shuffles and no shared-memory staging are
+// needed; x (<= 64 x K, L2 / L1 resident) is re-read by every CTA, W (the HBM stream) exactly once.
+template <typename T, int MT>
+__global__ void __launch_bounds__(256) dec_linear_kernel(const oasr_dec_linear_args a) {
+  __shared__ float s_stat[16 * MT][2];
+  __shared__ float s_red[8][16 * MT][17];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int n0 = blockIdx.x * 16;
+  const int K = a.K;
+  if (a.x_mode == X_LAYERNORM) {   // two-pass fp32 statistics per row (F.layer_norm(x.float()))
+    for (int row = warp; row < a.M; row += 8) {
+      const T* xr = static_cast<const T*>(a.x) + static_cast<int64_t>(row) * a.ldx;
+      float s = 0.f;
+      for (int k = lane * 8; k < K; k += 256) {
+        const uint4 u = *reinterpret_cast<const uint4*>(xr + k);
+        const float2 p0 = DT<T>::unpack2(u.x), p1 = DT<T>::unpack2(u.y), p2 = DT<T>::unpack2(u.z), p3 = DT<T>::unpack2(u.w);
+        s += (p0.x + p0.y) + (p1.x + p1.y) + (p2.x + p2.y) + (p3.x + p3.y);
+      }
+      const float mean = warp_sum(s) / static_cast<float>(K);
+      float q = 0.f;
+      for (int k = lane * 8; k < K; k += 256) {
+        const uint4 u = *reinterpret_cast<const uint4*>(xr + k);
+        const float2 p0 = DT<T>::unpack2(u.x), p1 = DT<T>::unpack2(u.y), p2 = DT<T>::unpack2(u.z), p3 = DT<T>::unpack2(u.w);
+        const float d0 = p0.x - mean, d1 = p0.y - mean, d2 = p1.x - mean, d3 = p1.y - mean;
+        const float d4 = p2.x - mean, d5 = p2.y - mean, d6 = p3.x - mean, d7 = p3.y - mean;
+        q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3) + (d4 * d4 + d5 * d5) + (d6 * d6 + d7 * d7);
+      }
+      const float var = warp_sum(q) / static_cast<float>(K);
+      if (lane == 0) { s_stat[row][0] = mean; s_stat[row][1] = rsqrtf(var + a.ln_eps); }
+    }
+    __syncthreads();
+  }
+  float acc[MT][2][4];
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+
+  const T* W = static_cast<const T*>(a.W);
+  const int r0 = n0 + g, r1 = n0 + 8 + g;
+  const T* w0 = W + static_cast<int64_t>(r0 < a.N ? r0 : 0) * K + 8 * t;
+  const T* w1 = W + static_cast<int64_t>(r1 < a.N ? r1 : 0) * K + 8 * t;
+  const bool ok0 = r0 < a.N, ok1 = r1 < a.N;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  int k0 = warp * 32;
+  uint4 b0 = zero, b1 = zero;
+  if (k0 < K) {
+    b0 = ok0 ? __ldg(reinterpret_cast<const uint4*>(w0 + k0)) : zero;
+    b1 = ok1 ? __ldg(reinterpret_cast<const uint4*>(w1 + k0)) : zero;
+  }
+  for (; k0 < K; k0 += 256) {
+    const int kn = k0 + 256;
+    uint4 nb0 = zero, nb1 = zero;
+    if (kn < K) {   // the HBM stream runs one step ahead of the MMAs
+      nb0 = ok0 ? __ldg(reinterpret_cast<const uint4*>(w0 + kn)) : zero;
+      nb1 = ok1 ? __ldg(reinterpret_cast<const uint4*>(w1 + kn)) : zero;
+    }
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+      const uint4 xa = load_x8<T>(a, s_stat, i * 16 + g, k0 + 8 * t);
+      const uint4 xb = load_x8<T>(a, s_stat, i * 16 + 8 + g, k0 + 8 * t);
+      DT<T>::mma(acc[i][0], xa.x, xb.x, xa.y, xb.y, b0.x, b0.y);
+      DT<T>::mma(acc[i][0], xa.z, xb.z, xa.w, xb.w, b0.z, b0.w);
+      DT<T>::mma(acc[i][1], xa.x, xb.x, xa.y, xb.y, b1.x, b1.y);
+      DT<T>::mma(acc[i][1], xa.z, xb.z, xa.w, xb.w, b1.z, b1.w);
+    }
+    b0 = nb0; b1 = nb1;
+  }
+  // fixed-order reduction over the 8 K slices (deterministic), then the epilogue
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      s_red[warp][i * 16 + g][j * 8 + 2 * t] = acc[i][j][0];
+      s_red[warp][i * 16 + g][j * 8 + 2 * t + 1] = acc[i][j][1];
+      s_red[warp][i * 16 + 8 + g][j * 8 + 2 * t] = acc[i][j][2];
+      s_red[warp][i * 16 + 8 + g][j * 8 + 2 * t + 1] = acc[i][j][3];
+    }
+  __syncthreads();
+  const int pos = (a.epi == EPI_QKV_SCATTER) ? *a.pos_ptr : 0;
+  for (int idx = threadIdx.x; idx < a.M * 16; idx += 256) {
+    const int row = idx >> 4, col = idx & 15, n = n0 + col;
+    if (n >= a.N) continue;
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += s_red[w][row][col];
+    if (a.epi == EPI_LOGITS_F32) {   // (x @ E^T).float(): the matmul output is rounded to T first (inf_model.py:357-360)
+      static_cast<float*>(a.out)[static_cast<int64_t>(row) * a.ldo + n] = rnd<T>(v);
+      continue;
+    }
+    if (a.bias) v += rnd<T>(a.bias[n]);                                 // bias.to(x.dtype) (inf_model.py:56-60)
+    float y = rnd<T>(v);
+    if (a.epi == EPI_GELU) y = gelu_exact(y);
+    if (a.epi == EPI_RESIDUAL) y = DT<T>::to_f(static_cast<const T*>(a.res)[static_cast<int64_t>(row) * a.ldres + n]) + y;
+    const T o = DT<T>::from_f(y);
+    if (a.epi == EPI_QKV_SCATTER) {   // [q | k | v]: q to scratch, k / v appended in place to the static self-attention cache
+      const int d = a.N / 3;
+      if (n < d) static_cast<T*>(a.out)[static_cast<int64_t>(row) * a.ldo + n] = o;
+      else if (n < 2 * d) static_cast<T*>(a.k_cache)[(static_cast<int64_t>(row) * a.cache_len + pos) * d + (n - d)] = o;
+      else static_cast<T*>(a.v_cache)[(static_cast<int64_t>(row) * a.cache_len + pos) * d + (n - 2 * d)] = o;
+    } else {
+      static_cast<T*>(a.out)[static_cast<int64_t>(row) * a.ldo + n] = o;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------- attention
+// scores[n, h, j] = float(round_T( sum_c round_T(q[c] * hd^-.25) * round_T(k_j[c] * hd^-.25) ))    (inf_model.py:176-181)
+// grid (splits, H, N), 128 threads: 8 lanes per key row (16 bytes = 8 dims each), 16 keys per pass.
+template <typename T>
+__global__ void __launch_bounds__(128) dec_attn_scores_kernel(const oasr_dec_attn_args a) {
+  const int s = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
+  const int nkeys = a.pos_ptr ? (*a.pos_ptr + 1) : a.n_keys;
+  const int per = (nkeys + gridDim.x - 1) / gridDim.x;
+  const int j0 = s * per, j1 = min(nkeys, j0 + per);
+  const int c8 = threadIdx.x & 7, slot = threadIdx.x >> 3;
+  const float scale = a.scale;
+  float qs[8];
+  {
+    const uint4 u = *reinterpret_cast<const uint4*>(static_cast<const T*>(a.q) + static_cast<int64_t>(n) * a.ldq + h * 64 + c8 * 8);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 p = DT<T>::unpack2(w[i]);
+      qs[2 * i] = rnd<T>(p.x * scale); qs[2 * i + 1] = rnd<T>(p.y * scale);
+    }
+  }
+  const T* kb = static_cast<const T*>(a.k) + static_cast<int64_t>(n) * a.kv_seq_stride + h * 64 + c8 * 8;
+  float* out = a.scores + (static_cast<int64_t>(n) * gridDim.y + h) * a.scores_ld;
+  for (int jb = j0; jb < j1; jb += 64) {   // 4 independent 16-byte loads in flight per thread
+    uint4 u[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int j = jb + r * 16 + slot;
+      u[r] = (j < j1) ? __ldg(reinterpret_cast<const uint4*>(kb + static_cast<int64_t>(j) * a.kv_row_stride)) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const uint32_t w[4] = {u[r].x, u[r].y, u[r].z, u[r].w};
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 p = DT<T>::unpack2(w[i]);
+        acc = fmaf(qs[2 * i], rnd<T>(p.x * scale), acc);
+        acc = fmaf(qs[2 * i + 1], rnd<T>(p.y * scale), acc);
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      const int j = jb + r * 16 + slot;
+      if (c8 == 0 && j < j1) out[j] = rnd<T>(acc);
+    }
+  }
+}
+
+// partial[s, n, h*64 + c] = sum_{j in split s} float(round_T(softmax(scores)[j])) * v_j[c]   (fp32; the consumer adds the
+// splits in order and rounds once = the single rounding of `w @ v`).  Every CTA first derives the row maximum and the
+// normaliser from ALL scores of its (n, h) (<= 1500 floats, L2-resident), as F.softmax(qk.float()) does.
+template <typename T>
+__global__ void __launch_bounds__(128) dec_attn_pv_kernel(const oasr_dec_attn_args a) {
+  __shared__ float s_part[4];
+  __shared__ float s_o[4][64];
+  const int s = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
+  const int nkeys = a.pos_ptr ? (*a.pos_ptr + 1) : a.n_keys;
+  const int per = (nkeys + gridDim.x - 1) / gridDim.x;
+  const int j0 = s * per, j1 = min(nkeys, j0 + per);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* sc = a.scores + (static_cast<int64_t>(n) * gridDim.y + h) * a.scores_ld;
+  float m = -INFINITY;
+  for (int j = threadIdx.x; j < nkeys; j += 128) m = fmaxf(m, sc[j]);
+  m = warp_max(m);
+  if (lane == 0) s_part[warp] = m;
+  __syncthreads();
+  m = fmaxf(fmaxf(s_part[0], s_part[1]), fmaxf(s_part[2], s_part[3]));
+  __syncthreads();
+  float l = 0.f;
+  for (int j = threadIdx.x; j < nkeys; j += 128) l += expf(sc[j] - m);
+  l = warp_sum(l);
+  if (lane == 0) s_part[warp] = l;
+  __syncthreads();
+  l = (s_part[0] + s_part[1]) + (s_part[2] + s_part[3]);
+  const float inv_l = 1.0f / l;
+
+  const int c8 = threadIdx.x & 7, slot = threadIdx.x >> 3;
+  const T* vb = static_cast<const T*>(a.v) + static_cast<int64_t>(n) * a.kv_seq_stride + h * 64 + c8 * 8;
+  float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int jb = j0; jb < j1; jb += 64) {
+    uint4 u[4];
+    float p[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int j = jb + r * 16 + slot;
+      const bool ok = j < j1;
+      u[r] = ok ? __ldg(reinterpret_cast<const uint4*>(vb + static_cast<int64_t>(j) * a.kv_row_stride)) : make_uint4(0, 0, 0, 0);
+      p[r] = ok ? rnd<T>(expf(sc[j] - m) * inv_l) : 0.f;            // softmax(...).to(q.dtype)
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const uint32_t w[4] = {u[r].x, u[r].y, u[r].z, u[r].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 vv = DT<T>::unpack2(w[i]);
+        o[2 * i] = fmaf(p[r], vv.x, o[2 * i]);
+        o[2 * i + 1] = fmaf(p[r], vv.y, o[2 * i + 1]);
+      }
+    }
+  }
+  // 16 key slots -> one: lanes with equal c8 inside the warp (xor 8, 16), then the 4 warps through shared memory
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    o[i] += __shfl_xor_sync(0xffffffffu, o[i], 8);
+    o[i] += __shfl_xor_sync(0xffffffffu, o[i], 16);
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_o[warp][lane * 8 + i] = o[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int c = threadIdx.x;
+    const float v = (s_o[0][c] + s_o[1][c]) + (s_o[2][c] + s_o[3][c]);
+    a.out_partial[(static_cast<int64_t>(s) * gridDim.z + n) * a.ld_out + h * 64 + c] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------- sampling
+// One block per sequence over its fp32 logits row (whisper/decoding.py: SuppressBlank, SuppressTokens, GreedyDecoder.update):
+//   * at pos == sot_index: no_speech_prob = softmax(raw logits)[no_speech]                       (DecodingTask._main_loop)
+//   * suppress[v] != 0 -> -inf; at the first sampled position also `blank` and `eot`            (SuppressTokens / SuppressBlank)
+//   * next = argmax (lowest index on ties); logprob = logit[next] - logsumexp(filtered row)
+//   * sum_logprobs += logprob unless the previous token is eot; rows whose previous token is eot keep emitting eot
+// Positions before sample_begin - 1 are teacher-forced: nothing is written there.
+__global__ void __launch_bounds__(256) dec_sample_kernel(const oasr_dec_sample_args a) {
+  __shared__ float s_f[8];
+  __shared__ int s_i[8];
+  __shared__ float s_bcast[2];
+  const int n = blockIdx.x;
+  const int pos = *a.pos_ptr;
+  const float* row = a.logits + static_cast<int64_t>(n) * a.ld_logits;
+  const int V = a.n_vocab;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool first = (pos == a.sample_begin - 1);
+  const bool sampling = pos >= a.sample_begin - 1;
+  const bool want_raw = (pos == a.sot_index);
+  if (!sampling && !want_raw) return;
+
+  // pass 1: maxima (raw and filtered) and the filtered argmax
+  float mraw = -INFINITY, mf = -INFINITY;
+  int arg = V;
+  for (int v = threadIdx.x; v < V; v += 256) {
+    const float x = row[v];
+    mraw = fmaxf(mraw, x);
+    const bool sup = a.suppress[v] != 0 || (first && a.suppress_blank && (v == a.blank || v == a.eot));
+    if (!sup && (x > mf || (x == mf && v < arg))) { mf = x; arg = v; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, mf, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (om > mf || (om == mf && oa < arg)) { mf = om; arg = oa; }
+    mraw = fmaxf(mraw, __shfl_xor_sync(0xffffffffu, mraw, o));
+  }
+  if (lane == 0) { s_f[warp] = mf; s_i[warp] = arg; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float bm = s_f[0]; int ba = s_i[0];
+    for (int w = 1; w < 8; ++w)
+      if (s_f[w] > bm || (s_f[w] == bm && s_i[w] < ba)) { bm = s_f[w]; ba = s_i[w]; }
+    s_bcast[0] = bm; s_i[0] = ba;
+  }
+  __syncthreads();
+  mf = s_bcast[0]; arg = s_i[0];
+  __syncthreads();
+  if (lane == 0) s_f[warp] = mraw;
+  __syncthreads();
+  mraw = fmaxf(fmaxf(fmaxf(s_f[0], s_f[1]), fmaxf(s_f[2], s_f[3])), fmaxf(fmaxf(s_f[4], s_f[5]), fmaxf(s_f[6], s_f[7])));
+  __syncthreads();
+
+  // pass 2: normalisers
+  float sraw = 0.f, sf = 0.f;
+  for (int v = threadIdx.x; v < V; v += 256) {
+    const float x = row[v];
+    sraw += expf(x - mraw);
+    const bool sup = a.suppress[v] != 0 || (first && a.suppress_blank && (v == a.blank || v == a.eot));
+    if (!sup) sf += expf(x - mf);
+  }
+  sraw = warp_sum(sraw); sf = warp_sum(sf);
+  if (lane == 0) { s_f[warp] = sf; }
+  __syncthreads();
+  float tf = 0.f;
+  for (int w = 0; w < 8; ++w) tf += s_f[w];
+  __syncthreads();
+  if (lane == 0) { s_f[warp] = sraw; }
+  __syncthreads();
+  float traw = 0.f;
+  for (int w = 0; w < 8; ++w) traw += s_f[w];
+
+  if (threadIdx.x == 0) {
+    if (want_raw) a.no_speech_prob[n] = expf(row[a.no_speech] - mraw) / traw;
+    if (sampling) {
+      const int prev = a.tokens[static_cast<int64_t>(n) * a.ld_tokens + pos];
+      const bool finished = (prev == a.eot);
+      const float logprob = -logf(tf);            // logit[arg] - (mf + log sum exp(x - mf)), logit[arg] == mf
+      if (!finished) a.sum_logprobs[n] += logprob;
+      const int next = finished ? a.eot : arg;
+      a.tokens[static_cast<int64_t>(n) * a.ld_tokens + pos + 1] = next;
+      if (next != a.eot) atomicAdd(a.n_unfinished, 1);
+    }
+  }
+}
+
+// pos += 1; done = (every sequence's last token is eot) -- the stop test of DecodingTask._main_loop, kept on the device
+__global__ void dec_advance_kernel(int32_t* pos_ptr, int32_t* n_unfinished, int32_t* done_flag, int sample_begin) {
+  const int pos = *pos_ptr;
+  if (pos >= sample_begin - 1) *done_flag = (*n_unfinished == 0) ? 1 : 0;
+  *n_unfinished = 0;
+  *pos_ptr = pos + 1;
+}
+
+template <typename TI, typename TO>
+__global__ void convert_kernel(const TI* __restrict__ src, TO* __restrict__ dst, int64_t n) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    dst[i] = static_cast<TO>(static_cast<float>(src[i]));
+}
+
+template <typename T, int MT>
+int launch_linear(const oasr_dec_linear_args& a, cudaStream_t st) {
+  dec_linear_kernel<T, MT><<<(unsigned)ceil_div(a.N, 16), 256, 0, st>>>(a);
+  OASR_LAUNCH_CHECK();
+  return OASR_OK;
+}
+template <typename T>
+int dispatch_linear(const oasr_dec_linear_args& a, cudaStream_t st) {
+  if (a.M <= 16) return launch_linear<T, 1>(a, st);
+  if (a.M <= 32) return launch_linear<T, 2>(a, st);
+  return launch_linear<T, 4>(a, st);
+}
+
+}  // namespace
+}  // namespace oasr
+
+using namespace oasr;
+
+extern "C" int oasr_dec_embed(const int32_t* tokens, int64_t ld_tokens, const int32_t* pos_ptr, const float* emb, const float* pos_emb,
+                              void* x, int64_t n_seq, int64_t d, int64_t n_vocab, int dtype, void* stream) {
+  OASR_REQUIRE(n_seq > 0 && d > 0 && tokens && pos_ptr && emb && pos_emb && x, "dec_embed: bad arguments");
+  if (dtype == OASR_DTYPE_F16)
+    dec_embed_kernel<__half><<<(unsigned)n_seq, 128, 0, (cudaStream_t)stream>>>(tokens, ld_tokens, pos_ptr, emb, pos_emb, (__half*)x, (int)d, (int)n_vocab);
+  else
+    dec_embed_kernel<bf16><<<(unsigned)n_seq, 128, 0, (cudaStream_t)stream>>>(tokens, ld_tokens, pos_ptr, emb, pos_emb, (bf16*)x, (int)d, (int)n_vocab);
+  OASR_LAUNCH_CHECK();
+  return OASR_OK;
+}
+
+extern "C" int oasr_dec_linear(const oasr_dec_linear_args* a, void* stream) {
+  OASR_REQUIRE(a != nullptr, "dec_linear: null arguments");
+  OASR_REQUIRE(a->M >= 1 && a->M <= 64, "dec_linear: 1 <= M <= 64 sequences (got %d)", a->M);
+  OASR_REQUIRE(a->N >= 1 && a->K >= 32 && (a->K % 32) == 0, "dec_linear: K must be a multiple of 32 (got %d)", a->K);
+  OASR_REQUIRE(a->x && a->W && a->out, "dec_linear: null tensor");
+  OASR_REQUIRE(((uintptr_t)a->x & 15) == 0 && ((uintptr_t)a->W & 15) == 0, "dec_linear: x and W must be 16-byte aligned");
+  OASR_REQUIRE(a->x_mode >= 0 && a->x_mode <= 2 && a->epi >= 0 && a->epi <= 4, "dec_linear: bad mode");
+  OASR_REQUIRE(a->x_mode != X_LAYERNORM || (a->ln_gamma && a->ln_beta), "dec_linear: LayerNorm mode needs gamma / beta");
+  OASR_REQUIRE(a->x_mode != X_PARTIAL_SUM || a->n_partials >= 1, "dec_linear: partial-sum mode needs n_partials >= 1");
+  OASR_REQUIRE(a->x_mode == X_PARTIAL_SUM || (a->ldx % 8) == 0, "dec_linear: ldx must be a multiple of 8");
+  OASR_REQUIRE(a->epi != EPI_RESIDUAL || a->res, "dec_linear: residual epilogue needs res");
+  OASR_REQUIRE(a->epi != EPI_QKV_SCATTER || (a->k_cache && a->v_cache && a->pos_ptr && a->N % 3 == 0), "dec_linear: qkv scatter needs caches and pos");
+  if (a->dtype == OASR_DTYPE_F16) return dispatch_linear<__half>(*a, (cudaStream_t)stream);
+  if (a->dtype == OASR_DTYPE_BF16) return dispatch_linear<bf16>(*a, (cudaStream_t)stream);
+  OASR_REQUIRE(false, "dec_linear: unknown dtype %d", a->dtype);
+}
+
+extern "C" int oasr_dec_attention(const oasr_dec_attn_args* a, void* stream) {
+  OASR_REQUIRE(a != nullptr && a->q && a->k && a->v && a->scores && a->out_partial, "dec_attention: null tensor");
+  OASR_REQUIRE(a->n_seq >= 1 && a->n_head >= 1 && a->n_splits >= 1, "dec_attention: bad sizes");
+  OASR_REQUIRE(a->pos_ptr != nullptr || a->n_keys >= 1, "dec_attention: key count missing");
+  OASR_REQUIRE((a->ldq % 8) == 0 && (a->kv_row_stride % 8) == 0 && (a->kv_seq_stride % 8) == 0, "dec_attention: strides must be multiples of 8");
+  dim3 grid((unsigned)a->n_splits, (unsigned)a->n_head, (unsigned)a->n_seq);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->dtype == OASR_DTYPE_F16) {
+    dec_attn_scores_kernel<__half><<<grid, 128, 0, st>>>(*a);
+    dec_attn_pv_kernel<__half><<<grid, 128, 0, st>>>(*a);
+  } else if (a->dtype == OASR_DTYPE_BF16) {
+    dec_attn_scores_kernel<bf16><<<grid, 128, 0, st>>>(*a);
+    dec_attn_pv_kernel<bf16><<<grid, 128, 0, st>>>(*a);
+  } else {
+    OASR_REQUIRE(false, "dec_attention: unknown dtype %d", a->dtype);
+  }
+  OASR_LAUNCH_CHECK();
+  return OASR_OK;
+}
+
+extern "C" int oasr_dec_sample(const oasr_dec_sample_args* a, void* stream) {
+  OASR_REQUIRE(a != nullptr && a->logits && a->tokens && a->pos_ptr && a->suppress && a->sum_logprobs && a->no_speech_prob &&
+                   a->n_unfinished && a->done_flag, "dec_sample: null tensor");
+  OASR_REQUIRE(a->n_seq >= 1 && a->n_vocab >= 1, "dec_sample: bad sizes");
+  dec_sample_kernel<<<(unsigned)a->n_seq, 256, 0, (cudaStream_t)stream>>>(*a);
+  dec_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(a->pos_ptr, a->n_unfinished, a->done_flag, a->sample_begin);
+  OASR_LAUNCH_CHECK();
+  return OASR_OK;
+}
+
+extern "C" int oasr_convert(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream) {
+  OASR_REQUIRE(src && dst && n > 0, "convert: bad arguments");
+  const int blocks = (int)std::min<int64_t>(ceil_div(n, 256), (int64_t)num_sms() * 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (src_dtype == OASR_DTYPE_F32 && dst_dtype == OASR_DTYPE_F16) convert_kernel<float, __half><<<blocks, 256, 0, st>>>((const float*)src, (__half*)dst, n);
+  else if (src_dtype == OASR_DTYPE_F32 && dst_dtype == OASR_DTYPE_BF16) convert_kernel<float, bf16><<<blocks, 256, 0, st>>>((const float*)src, (bf16*)dst, n);
+  else if (src_dtype == OASR_DTYPE_BF16 && dst_dtype == OASR_DTYPE_F16) convert_kernel<bf16, __half><<<blocks, 256, 0, st>>>((const bf16*)src, (__half*)dst, n);
+  else if (src_dtype == OASR_DTYPE_F16 && dst_dtype == OASR_DTYPE_BF16) convert_kernel<__half, bf16><<<blocks, 256, 0, st>>>((const __half*)src, (bf16*)dst, n);
+  else OASR_REQUIRE(false, "convert: unsupported dtype pair %d -> %d", src_dtype, dst_dtype);
+  OASR_LAUNCH_CHECK();
+  return OASR_OK;
+}

@@ -24,6 +24,11 @@ from torch import Tensor
 if TYPE_CHECKING:
     from ._core import OLMoASRBase
 
+import os
+
+# OASR_DECODE_ENGINE=0 forces the generic hook-based loop below for every configuration (A/B runs, debugging)
+USE_ENGINE = os.environ.get("OASR_DECODE_ENGINE", "1") != "0"
+
 # ---- English-only vocabulary constants -------------------------------------------------
 EOT, SOT = 50256, 50257
 TRANSLATE, TRANSCRIBE, SOT_LM, SOT_PREV, NO_SPEECH, NO_TIMESTAMPS, TIMESTAMP_BEGIN = 50357, 50358, 50359, 50360, 50361, 50362, 50363
@@ -53,7 +58,7 @@ class DecodingOptions:
     suppress_blank: bool = True
     without_timestamps: bool = False
     max_initial_timestamp: Optional[float] = 1.0
-    fp16: bool = True  # accepted for API compatibility; this implementation always computes in bf16
+    fp16: bool = True  # decoder-step activation dtype: fp16 (upstream default) or, when False, bf16 (there are no fp32 kernels)
 
 
 @dataclass(frozen=True)
@@ -154,6 +159,8 @@ class DecodingTask:
             audio_features = model.encoder(mel)
         n_audio = audio_features.shape[0]
         dev = audio_features.device
+        if opt.temperature == 0 and self.ts_rules is None and USE_ENGINE and hasattr(model, "decode_engine"):
+            return self._run_on_device(audio_features, tokenizer)
         tokens = torch.tensor([self.initial_tokens], device=dev).repeat(n_audio, 1)
         sum_logprobs = torch.zeros(n_audio, device=dev)
         no_speech_probs = [np.nan] * n_audio
@@ -189,6 +196,27 @@ class DecodingTask:
             for h in hooks:
                 h.remove()
         tokens = F.pad(tokens, (0, 1), value=EOT)  # GreedyDecoder.finalize
+        return self._results(audio_features, tokens, sum_logprobs.tolist(), no_speech_probs, tokenizer)
+
+    def _run_on_device(self, audio_features: Tensor, tokenizer):
+        """Greedy decoding without timestamp rules (the short-form eval configuration, scripts/eval/eval.py:1846-1847): the
+        whole loop runs as replays of one CUDA graph (olmoasr_b200/decode_engine.py)."""
+        from .decode_engine import DecodeEngine
+
+        eng = self.model.decode_engine(torch.float16 if self.options.fp16 else torch.bfloat16)
+        toks, lps, nsp = [], [], []
+        for s in range(0, audio_features.shape[0], DecodeEngine.MAX_BATCH):
+            t, lp, ns, _ = eng.greedy(audio_features[s:s + DecodeEngine.MAX_BATCH], self.initial_tokens, self.sample_len, self.suppress,
+                                      self.options.suppress_blank, self.sot_index)
+            toks.append(t); lps += lp.tolist(); nsp += ns.tolist()
+        width = max(t.shape[1] for t in toks)
+        tokens = torch.cat([F.pad(t, (0, width - t.shape[1]), value=EOT) for t in toks], dim=0)
+        tokens = F.pad(tokens, (0, 1), value=EOT)  # GreedyDecoder.finalize
+        return self._results(audio_features, tokens, lps, nsp, tokenizer)
+
+    def _results(self, audio_features, tokens, sum_logprobs, no_speech_probs, tokenizer) -> List[DecodingResult]:
+        opt = self.options
+        n_audio = audio_features.shape[0]
         results = []
         for k in range(n_audio):
             seq = tokens[k, self.sample_begin:]

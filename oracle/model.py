@@ -224,6 +224,7 @@ def decoder_forward(sd, dims: Dims, tokens: Tensor, xa: Tensor, padding_mask: Op
         mask = padding_mask + causal_mask(dims.n_text_ctx if train_model else n_ctx)
     else:
         mask = causal_mask(dims.n_text_ctx)[:n_ctx, :n_ctx] if train_model else causal_mask(n_ctx)
+    mask = mask.to(x.device)   # the reference moves its mask to the activations' device too (inf_model.py:341-352)
     for i in range(dims.n_text_layer):
         x = _res_block(sd, f"decoder.blocks.{i}", dims.n_text_head, x, xa, mask=mask, sdpa=train_model, cache=cache)
     x = _layer_norm(sd, "decoder.ln", x)

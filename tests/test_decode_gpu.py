@@ -36,14 +36,29 @@ def test_greedy_token_ids_match_oracle():
     n_steps = 16
     with torch.no_grad():
         want, margins = OD.greedy_decode(sd, dims, mel, sample_len=n_steps, dtype=torch.bfloat16, return_margins=True)
-    res = decode(m, mel.cuda(), DecodingOptions(language="en", without_timestamps=True, sample_len=n_steps))
+    # fp16=False: bf16 decode, the dtype the CPU oracle loop runs in (fp16 is covered against the reference's GPU path in
+    # tests/test_decode_engine_gpu.py)
+    res = decode(m, mel.cuda(), DecodingOptions(language="en", without_timestamps=True, sample_len=n_steps, fp16=False))
     got = [r.tokens for r in res]
     print("min top-1/top-2 margin (oracle, bf16):", min(margins), "tokens:", got[0][:8])
     assert got == want
     assert all(isinstance(r.avg_logprob, float) and r.avg_logprob <= 0 for r in res)
     assert all(0.0 <= r.no_speech_prob <= 1.0 for r in res)
-    one = decode(m, mel[0].cuda(), DecodingOptions(without_timestamps=True, sample_len=4))
+    one = decode(m, mel[0].cuda(), DecodingOptions(without_timestamps=True, sample_len=4, fp16=False))
     assert one.tokens == want[0][:4]
+
+
+def test_generic_hook_loop_matches_the_engine(monkeypatch):
+    """The hook-based loop (sampling / timestamp rules / third-party callers) and the device-resident engine give the
+    same greedy ids: the static-buffer kv-cache store behaves like the reference's growing dict."""
+    from olmoasr_b200 import decoding as D
+
+    m, sd, dims, mel = _make(scale=6.0)
+    opts = D.DecodingOptions(language="en", without_timestamps=True, sample_len=10, fp16=False)
+    a = [r.tokens for r in D.decode(m, mel.cuda(), opts)]
+    monkeypatch.setattr(D, "USE_ENGINE", False)
+    b = [r.tokens for r in D.decode(m, mel.cuda(), opts)]
+    assert a == b
 
 
 def test_kv_cache_steps_equal_full_reforward():
@@ -63,6 +78,8 @@ def test_kv_cache_steps_equal_full_reforward():
             h.remove()
     assert len(cache) == 4 * dims.n_text_layer
     assert cache[m.decoder.blocks[0].attn.key].shape == (3, 5, 384)
+    assert cache[m.decoder.blocks[0].attn.key].data_ptr() == cache[m.decoder.blocks[0].attn.key][:, :1].data_ptr()
+    assert cache[m.decoder.blocks[0].attn.key].stride(0) == 448 * 384      # a view of the pre-allocated (B, 448, d) buffer: no torch.cat
     assert cache[m.decoder.blocks[0].cross_attn.key].shape == (3, 1500, 384)   # stored once, never concatenated
     ref = full.float()
     for got, sl in ((s1, slice(0, 3)), (s2, slice(3, 4)), (s3, slice(4, 5))):
