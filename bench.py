@@ -392,6 +392,137 @@ def our_arm(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# second half of BASELINE.json's metric: greedy-decode real-time factor (config 5: small, kv-cache decode, 1 GPU,
+# 1..64 concurrent 30 s clips; scripts/eval/eval.py:1846-1847 calls model.decode(mel, DecodingOptions(language="en",
+# without_timestamps=True)) -> up to n_text_ctx // 2 = 224 sampled tokens per clip)
+# ------------------------------------------------------------------------------------------------------------------
+RTF_METRIC = "greedy-decode RTF"
+RTF_BATCHES = (1, 2, 4, 8, 16, 32, 64)
+
+
+def cpu_decode_reference(variant: str, n_clips: int = 1, sample_len: int = 224):
+    """The reference's CPU path for config 5 (oracle port of inf_model.py + the upstream greedy loop), fp32, all host
+    threads: log-mel + encoder + `sample_len` kv-cache steps for `n_clips` clips.  Returns (RTF, seconds, threads)."""
+    from oracle import decoding as OD
+    from oracle import logmel
+    from oracle import model as OM
+    from olmoasr_b200 import synthetic as synth
+
+    threads = usable_cpus()
+    torch.set_num_threads(threads)
+    dims = OM.variant_dims(variant)
+    sd = OM.init_state_dict(dims, 0, train=False)
+    sd["decoder.positional_embedding"] = torch.randn(dims.n_text_ctx, dims.n_text_state, generator=torch.Generator().manual_seed(7)) * 0.01
+    wav = synth.waveforms(n_clips).numpy()
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        mel = torch.from_numpy(logmel.log_mel_spectrogram(wav))
+        OD.greedy_decode(sd, dims, mel, sample_len=sample_len, dtype=torch.float32)
+    sec = time.perf_counter() - t0
+    return sec / (n_clips * 30.0), sec, threads
+
+
+def rtf_reference_arm(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    rtf, sec, threads = cpu_decode_reference(args.variant_rtf, 1, 224)
+    line = {"impl": "reference", "metric": RTF_METRIC, "value": rtf, "unit": "s per s of audio", "n_gpus": args.gpus, "steps": 1,
+            "warmup": 0, "steps_requested": args.steps, "ms_per_step": sec * 1e3, "higher_is_better": False, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.variant_rtf} greedy kv-cache decode of 1 x 30 s synthetic clip, 224 sampled tokens (reference CPU path)",
+                       "parallelism": "cpu"},
+            "cpu_baseline": {"value": rtf, "unit": "s per s of audio", "cores": threads, "kind": "port",
+                             "sample": f"1 clip, log-mel + encoder + 224 greedy steps, fp32, {threads} threads ({sec:.1f} s)"},
+            "e2e": {"value": rtf, "unit": "s per s of audio", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def rtf_arm(args):
+    """`--metric rtf`: the RTF sweep on one GPU.  A "step" here is one complete decode of N concurrent clips (int16
+    waveform in pinned host memory -> H2D -> log-mel -> encoder -> cross K/V -> 1 + 224 graph replays -> token ids D2H)."""
+    import olmoasr_b200 as ob
+    from olmoasr_b200 import _lib
+    from olmoasr_b200 import synthetic as synth
+    from olmoasr_b200.decoding import DecodingOptions, DecodingTask
+    from olmoasr_b200.inf_model import OLMoASR
+
+    world, rank, local_rank, dev = _setup_dist()
+    variant = args.variant_rtf
+    dims = ob.VARIANT_TO_DIMS[variant]
+    torch.manual_seed(0)
+    with torch.device(dev):
+        model = OLMoASR(dims)
+    with torch.no_grad():
+        model.decoder.positional_embedding.normal_(0, 0.01)   # inf_model.py:307 leaves it uninitialised (checkpoints fill it)
+    dtype = torch.float16 if args.dtype == "fp16" else torch.bfloat16
+    eng = model.decode_engine(dtype)
+    opts = DecodingOptions(language="en", without_timestamps=True, fp16=(dtype == torch.float16))
+    task = DecodingTask(model, opts)
+    sample_len = task.sample_len
+    peaks = _peaks()
+    sweep = []
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = _lib.LAUNCH_COUNT
+    for n in RTF_BATCHES:
+        wav_h = synth.waveforms(n, rank=rank, int16=True).pin_memory()
+
+        def full_decode():
+            wav = wav_h.to(dev, non_blocking=True)
+            mel = ob.log_mel_spectrogram(wav)
+            with torch.no_grad():
+                xa = model.encoder(mel)
+            toks, lps, nsp, replays = eng.greedy(xa, task.initial_tokens, sample_len, task.suppress, opts.suppress_blank, task.sot_index)
+            return toks, replays
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            full_decode()
+        torch.cuda.synchronize()
+        reps = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            toks, replays = full_decode()       # ends with a D2H copy of the token ids: wall clock covers everything
+        wall = (time.perf_counter() - t0) / reps
+        # the replay loop alone (device time): graph replays back to back from a prepared state
+        eng.reset(n, torch.tensor([list(task.initial_tokens)], dtype=torch.int32).repeat(n, 1), None, task.suppress, opts.suppress_blank, task.sot_index)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(replays):
+            eng.replay(n)
+        e1.record()
+        torch.cuda.synchronize()
+        step_ms = e0.elapsed_time(e1) / replays
+        t_mid = len(task.initial_tokens) + sample_len // 2
+        gbs = eng.step_bytes(n, t_mid) / (step_ms * 1e-3) / 1e9
+        sweep.append({"n_clips": n, "rtf": wall / (n * 30.0), "wall_s": wall, "replays": replays, "ms_per_step": step_ms,
+                      "step_gb": eng.step_bytes(n, t_mid) / 1e9, "hbm_gbs": gbs, "hbm_frac": gbs / peaks["hbm_gbs"],
+                      "tokens_per_s": n * 1e3 / step_ms})
+    launches = _lib.LAUNCH_COUNT - launches0
+    clocks = sampler.stop()
+    best = sweep[-1]
+    line = {"metric": RTF_METRIC, "value": best["rtf"], "unit": "s per s of audio", "n_gpus": 1, "steps": max(1, min(args.steps, 3)),
+            "warmup": max(1, min(args.warmup, 2)), "ms_per_step": best["wall_s"] * 1e3, "higher_is_better": False, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"{variant} greedy kv-cache decode (BASELINE.json configs[4]): N concurrent 30 s synthetic clips, "
+                                   f"{sample_len} sampled tokens each (random-init weights never emit eot), value = RTF at N = {best['n_clips']}",
+                       "sweep": sweep, "launches_per_decode_step": eng.launches_per_step,
+                       "l2": "every step re-reads the decoder weights (278 MB) and N x 55 MB of cross K/V: > 126 MB L2 from N = 1"},
+            "e2e": {"value": best["rtf"], "unit": "s per s of audio", "h2d_bytes_per_step": best["n_clips"] * 480000 * 2,
+                    "d2h_bytes_per_step": best["n_clips"] * (len(task.initial_tokens) + sample_len) * 8},
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "decode step (dec_linear / dec_attn_scores / dec_attn_pv / dec_sample graph replay)",
+                         "achieved": best["hbm_gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": best["hbm_frac"], "traffic": None,
+                         "peak_source": peaks["source"], "algorithmic_bytes": "weights once + per sequence cross K/V of every layer + "
+                                                                                "self K/V so far + fp32 logits row (SURVEY.md 8(d))"}}
+    if not args.no_cpu_baseline:
+        rtf, sec, threads = cpu_decode_reference(variant, 1, 224)
+        line["cpu_baseline"] = {"value": rtf, "unit": "s per s of audio", "cores": threads, "kind": "port",
+                                "sample": f"1 clip, log-mel + encoder + 224 greedy steps, fp32, {threads} threads ({sec:.1f} s)"}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -402,8 +533,14 @@ def main():
     ap.add_argument("--batch-per-gpu", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--metric", default="train", choices=["train", "rtf"], help="train: clips/s (default, the driver's line); "
+                    "rtf: greedy-decode real-time factor sweep (BASELINE.json metric, second half)")
+    ap.add_argument("--variant-rtf", default="small")
+    ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"], help="decode activation dtype for --metric rtf")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.metric == "rtf":
+        (rtf_reference_arm if args.impl == "reference" else rtf_arm)(args)
+    elif args.impl == "reference":
         reference_arm(args)
     elif args.impl == "torch_gpu":
         torch_gpu_arm(args)
