@@ -125,6 +125,48 @@ def test_load_model_reads_reference_checkpoints(tmp_path):
         ob.load_model("no-such-model", device="cpu")
 
 
+def _small_dims():
+    from olmoasr_b200.config.model_dims import ModelDimensions
+    return ModelDimensions(80, 1500, 64, 1, 2, 51864, 448, 64, 1, 2)
+
+
+def test_checkpoint_writer_and_gen_inf_ckpt_round_trip(tmp_path):
+    """what save_ckpt writes (train_timestamps.py:930-955, both flavours) loads back into the training model,
+    converts with gen_inf_ckpt (scripts/eval/gen_inf_ckpt.py:4-11) and loads into the inference model through load_model --
+    also from a model whose parameters live in slabs."""
+    import olmoasr_b200 as ob
+    from olmoasr_b200 import checkpoint as C
+    from olmoasr_b200.model import OLMoASR
+
+    torch.manual_seed(0)
+    m = OLMoASR(_small_dims())
+    m.use_slabs()
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-3)
+    for flavour, ddp in (("non_ddp", False), ("ddp", True)):
+        path = str(tmp_path / f"latesttrain_00000007_tiny_x_{flavour}.pt")
+        C.save_ckpt(path, m, opt, global_step=7, epoch=1, best_eval_wer=0.5, ddp_names=ddp)
+        ck = torch.load(path, weights_only=False)
+        assert set(ck) == {"global_step", "local_step", "epoch", "best_eval_wer", "model_state_dict", "optimizer_state_dict",
+                           "scaler_state_dict", "scheduler_state_dict", "dims"}
+        keys = list(ck["model_state_dict"])
+        assert all(k.startswith("module.") for k in keys) == ddp
+        sizes = {v.untyped_storage().nbytes() for v in ck["model_state_dict"].values()}
+        assert max(sizes) == ck["model_state_dict"][("module." if ddp else "") + "decoder.token_embedding.weight"].numel() * 4   # no slab-sized storages
+        torch.manual_seed(1)
+        m2 = OLMoASR(_small_dims())
+        got = C.load_ckpt(path, m2)
+        assert got["global_step"] == 7 and all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+        assert ob.load_model(path, device="cpu").state_dict().keys() == m.state_dict().keys()
+        inf = C.gen_inf_ckpt(path, str(tmp_path / f"inf_{flavour}.pt"))
+        ic = torch.load(inf, weights_only=False)
+        assert isinstance(ic["dims"], dict) and ic["model_state_dict"]["decoder.token_embedding.weight"].shape[0] == 51864
+        mi = ob.load_model(inf, device="cpu", inference=True)
+        assert torch.equal(mi.decoder.token_embedding.weight, m.decoder.token_embedding.weight[:-1])
+        assert torch.equal(mi.encoder.conv1.weight, m.encoder.conv1.weight)
+    with pytest.raises(ValueError, match="not a training checkpoint"):
+        C.gen_inf_ckpt(inf, str(tmp_path / "twice.pt"))
+
+
 # ---------------------------------------------------------------------------------------------- 2-rank gloo
 def _free_port():
     s = socket.socket()
@@ -238,10 +280,6 @@ def test_blockwise_grad_reducer_matches_ddp_averaging_world2_gloo(tmp_path, coal
 
 
 # ---------------------------------------------------------------------------------------------- parameter slabs (host logic)
-def _small_dims():
-    from olmoasr_b200.config.model_dims import ModelDimensions
-    return ModelDimensions(80, 1500, 64, 1, 2, 51864, 448, 64, 1, 2)
-
 
 def test_slab_layout_keeps_the_state_dict_and_gives_fused_views():
     from olmoasr_b200.model import OLMoASR
