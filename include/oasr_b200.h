@@ -76,10 +76,13 @@ OASR_API int oasr_gemm_bf16(const void* A, int64_t lda, int a_layout, const void
  * olmoasr/transcribe.py:148.  wave: (batch, n_samples) f32 or int16 (int16 is scaled by 1/32768 like
  * train_timestamps.py:196); out: (batch, n_mels, n_samples/160) f32; clip_max: (batch,) f32 scratch.
  * window/cos_tab/sin_tab: 400 f32 each (Hann window, cos/sin(2 pi i/400)); filters: (n_mels, 201) f32 with
- * non-zero column range [klo[m], khi[m]) per band.  The dynamic-range floor is per clip. */
+ * non-zero column range [klo[m], khi[m]) per band.  The dynamic-range floor is per clip.
+ * n_samples is the row length (a multiple of 640); n_valid <= n_samples (0 = n_samples) the true sample count of every
+ * clip: the end reflection of torch.stft(center=True) happens at n_valid and frames >= n_valid/160 are padding (-inf
+ * before, floor after the final pass), so recordings of any length give upstream's n // 160 frames exactly. */
 OASR_API int oasr_logmel(const void* wave, int in_is_int16, const float* window, const float* cos_tab,
                          const float* sin_tab, const float* filters, const int* klo, const int* khi, float* out,
-                         float* clip_max, int64_t batch, int64_t n_samples, int64_t n_mels, void* stream);
+                         float* clip_max, int64_t batch, int64_t n_samples, int64_t n_mels, int64_t n_valid, void* stream);
 
 /* ---- LayerNorm (olmoasr/model.py:25-39: F.layer_norm(x.float()).type(x.dtype)) -------------------
  * x, y, dy, dx, dresidual: (rows, d) bf16; weight/bias/dweight/dbias: (d,) f32; mean/rstd: (rows,) f32

@@ -63,7 +63,7 @@ _SIGNATURES = {
     "oasr_device_sm_count": [],
     "oasr_gemm_set_sm_budget": [c_int],
     "oasr_logmel": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                    c_i64, c_i64, c_i64, c_void_p],
+                    c_i64, c_i64, c_i64, c_i64, c_void_p],
     "oasr_layernorm_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_float, c_void_p],
     "oasr_layernorm_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                            c_i64, c_i64, c_void_p],

@@ -109,10 +109,8 @@ def log_mel_spectrogram(audio: Union[str, np.ndarray, torch.Tensor], n_mels: int
     """Log-mel spectrogram of a waveform (n,) or batch (B, n): float32 or int16 samples at 16 kHz.
 
     Returns (n_mels, n // 160) or (B, n_mels, n // 160) float32 on the CUDA device, n = samples + padding, any length
-    >= 400 (upstream: n // 160 frames for every n).  The kernel frames whole 640-sample groups, so other lengths are
-    zero-extended to the next multiple of 640 and the extra frames dropped: exact whenever the recording ends in
-    silence -- `transcribe` always appends 30 s of zeros (olmoasr/transcribe.py:148) -- and otherwise only the last two
-    frames see zeros where upstream's reflect padding would mirror the final 200 samples."""
+    >= 400 (upstream: n // 160 frames for every n).  Rows are padded to whole 640-sample groups for the kernel, which is
+    told the true length: the end reflection of torch.stft happens there, padded frames are dropped."""
     if not torch.is_tensor(audio):
         if isinstance(audio, str):
             audio = load_audio(audio)
@@ -144,7 +142,7 @@ def log_mel_spectrogram(audio: Union[str, np.ndarray, torch.Tensor], n_mels: int
     out = torch.empty((B, n_mels, n // HOP_LENGTH), device=audio.device, dtype=torch.float32)
     clip_max = torch.empty(B, device=audio.device, dtype=torch.float32)
     call("oasr_logmel", ptr(audio), int(audio.dtype == torch.int16), ptr(window), ptr(cos_t), ptr(sin_t), ptr(filt),
-         ptr(klo), ptr(khi), ptr(out), ptr(clip_max), B, n, n_mels, stream())
+         ptr(klo), ptr(khi), ptr(out), ptr(clip_max), B, n, n_mels, n_true, stream())
     if n != n_true:
         out = out[:, :, : n_true // HOP_LENGTH]
     return out[0] if squeeze else out

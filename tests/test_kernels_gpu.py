@@ -376,12 +376,15 @@ def test_logmel_matches_oracle(golden_dir):
     assert np.abs(a - b).max() < 1e-4
     short = audio.log_mel_spectrogram(audio.pad_or_trim(wav[0, :51237].cuda()))
     assert short.shape == (80, 3000)
-    # any length (ffmpeg output is arbitrary): n // 160 frames like upstream; with transcribe's 30 s of appended zeros the
-    # result is exact, without it only the last two frames may differ (zero extension instead of the end reflection)
+    # any length (ffmpeg output is arbitrary): n // 160 frames like upstream, end reflection at the true last sample
     odd = wav[0, :51237]
     a = audio.log_mel_spectrogram(odd.cuda(), padding=480000).cpu().numpy()
     b = logmel.log_mel_spectrogram(np.pad(odd.numpy(), (0, 480000)))
     assert a.shape == b.shape == (80, (51237 + 480000) // 160) and np.abs(a - b).max() < 1e-4
-    c = audio.log_mel_spectrogram(odd.cuda()).cpu().numpy()
-    e = logmel.log_mel_spectrogram(odd.numpy())
-    assert c.shape == e.shape == (80, 51237 // 160) and np.abs(c[:, :-2] - e[:, :-2]).max() < 1e-4
+    for n in (51237, 51200, 640 * 7 + 1, 401):
+        c = audio.log_mel_spectrogram(wav[0, :n].cuda()).cpu().numpy()
+        e = logmel.log_mel_spectrogram(wav[0, :n].numpy())
+        assert c.shape == e.shape == (80, n // 160) and np.abs(c - e).max() < 1e-4, n
+    tone = (0.3 * np.sin(2 * np.pi * 440.0 * np.arange(480000) / 16000.0)).astype(np.float32)     # a spectral line: FFT leakage check
+    t = audio.log_mel_spectrogram(torch.from_numpy(tone).cuda()).cpu().numpy()
+    assert np.abs(t[:, ::7] - gold["tone"]).max() < 2e-4
