@@ -246,7 +246,7 @@ class LayerNorm(nn.LayerNorm):
 
     def forward(self, x: Tensor) -> Tensor:
         shp = x.shape
-        y = K.layernorm_fwd(_as_bf16_2d(x), self.weight, self.bias, self.eps, want_stats=False)
+        y = K.layernorm_fwd(_as_bf16_2d(x), _f32(self.weight), _f32(self.bias), self.eps, want_stats=False)
         return y.view(shp)
 
 
@@ -263,11 +263,13 @@ class Linear(nn.Linear):
     def weight_bf16(self) -> Tensor:
         if self._slab_view is not None:
             return self._slab_view
+        if self.weight.dtype == torch.bfloat16:      # FSDP bf16 param_dtype: the unsharded view IS the operand (never cached)
+            return self.weight.detach()
         return self._shadow.get((self.weight,), lambda: K.cast_bf16(self.weight.detach().contiguous()))
 
     def forward(self, x: Tensor) -> Tensor:  # inference / hook path (no autograd through the kernels)
         shp = x.shape
-        y = linear_fwd(_as_bf16_2d(x), self.weight_bf16(), self.bias)
+        y = linear_fwd(_as_bf16_2d(x), self.weight_bf16(), None if self.bias is None else _f32(self.bias))
         return y.view(*shp[:-1], self.out_features)
 
 
@@ -282,6 +284,8 @@ class Conv1d(nn.Conv1d):
         self._shadow = _ShadowCache()
 
     def weight_bf16(self) -> Tensor:  # (C_out, 3*C_in) with column = k*C_in + c
+        if not _is_master(self.weight):
+            return K.cast_conv_weight(_f32(self.weight).contiguous())
         return self._shadow.get((self.weight,), lambda: K.cast_conv_weight(self.weight.detach().contiguous()))
 
 
@@ -298,6 +302,19 @@ def _as_bf16_2d(x: Tensor) -> Tensor:
     if x.dtype != torch.bfloat16:
         x = x.to(torch.bfloat16)
     return x.reshape(-1, x.shape[-1]).contiguous()
+
+
+def _f32(p: Tensor) -> Tensor:
+    """fp32 view of a vector parameter / buffer.  Parameters are fp32 masters except under FSDP MixedPrecision(param_dtype=
+    bf16) (scripts/training/train_fsdp_timestamps.py:2588-2615), where the unsharded views are bf16: converted per call."""
+    p = p.detach()
+    if p.dtype == torch.float32:
+        return p
+    return K.convert(p.contiguous(), dtype=torch.float32)
+
+
+def _is_master(p: Tensor) -> bool:
+    return p.dtype == torch.float32
 
 
 class MultiHeadAttention(nn.Module):
@@ -333,11 +350,22 @@ class MultiHeadAttention(nn.Module):
         def build():
             d = self.query.weight.shape[0]
             w = torch.empty((3 * d, d), device=ps[0].device, dtype=torch.bfloat16)
+            b = torch.zeros(3 * d, device=ps[0].device, dtype=torch.float32)
             for i, p in enumerate(ps[:3]):
-                K.cast_bf16(p.detach().contiguous(), w[i * d:(i + 1) * d])
-            b = torch.cat([ps[3].detach().float(), torch.zeros(d, device=ps[0].device), ps[4].detach().float()])
+                if _is_master(p):
+                    K.cast_bf16(p.detach().contiguous(), w[i * d:(i + 1) * d])
+                else:
+                    w[i * d:(i + 1) * d].copy_(p.detach())     # bf16 unsharded FSDP view: a device-to-device copy
+            for p, sl in ((ps[3], slice(0, d)), (ps[4], slice(2 * d, 3 * d))):
+                if _is_master(p):
+                    b[sl].copy_(p.detach())
+                else:
+                    K.convert(p.detach().contiguous(), b[sl])
             return w, b
 
+        if not _is_master(ps[0]):
+            with torch.no_grad():
+                return build()                                  # transient FSDP views: nothing to key a cache on
         return self._fused.get(ps, build)
 
     def fused_kv(self):
@@ -385,23 +413,23 @@ class _BlockFn(torch.autograd.Function):
         if xa is not None:   # the cross-attention K/V projection only needs the encoder output: side stream, joined below
             kvc = torch.empty((xa.shape[0], 2 * d), device=x.device, dtype=torch.bfloat16)
             side.run(lambda: linear_fwd(xa, sh["wckv"], sh["bckv"], out=kvc))
-        ln1, mean1, rstd1 = K.layernorm_fwd(x, blk.attn_ln.weight, blk.attn_ln.bias)
+        ln1, mean1, rstd1 = K.layernorm_fwd(x, sh["ln1w"], sh["ln1b"])
         qkv = linear_fwd(ln1, sh["wqkv"], sh["bqkv"])
         ao, lse = K.attention_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], B, H, T, T, causal=causal, kv_len=kv_len)
-        x1 = linear_fwd(ao, sh["wo"], blk.attn.out.bias, epi=K.EPI_BF16_RESIDUAL, aux=x)
+        x1 = linear_fwd(ao, sh["wo"], sh["bo"], epi=K.EPI_BF16_RESIDUAL, aux=x)
         saved = [x, mean1, rstd1, ln1, qkv, ao, lse, x1]
         if xa is not None:
-            lnc, meanc, rstdc = K.layernorm_fwd(x1, blk.cross_attn_ln.weight, blk.cross_attn_ln.bias)
-            qc = linear_fwd(lnc, sh["wcq"], blk.cross_attn.query.bias)
+            lnc, meanc, rstdc = K.layernorm_fwd(x1, sh["lncw"], sh["lncb"])
+            qc = linear_fwd(lnc, sh["wcq"], sh["bcq"])
             side.join()
             co, lsec = K.attention_fwd(qc, kvc[:, :d], kvc[:, d:], B, H, T, Ta)
-            x2 = linear_fwd(co, sh["wco"], blk.cross_attn.out.bias, epi=K.EPI_BF16_RESIDUAL, aux=x1)
+            x2 = linear_fwd(co, sh["wco"], sh["bco"], epi=K.EPI_BF16_RESIDUAL, aux=x1)
             saved += [xa, meanc, rstdc, lnc, qc, kvc, co, lsec, x2]
         else:
             x2 = x1
-        ln2, mean2, rstd2 = K.layernorm_fwd(x2, blk.mlp_ln.weight, blk.mlp_ln.bias)
-        h, g = linear_fwd(ln2, sh["w1"], blk.mlp[0].bias, epi=K.EPI_BF16_GELU)
-        x3 = linear_fwd(g, sh["w2"], blk.mlp[2].bias, epi=K.EPI_BF16_RESIDUAL, aux=x2)
+        ln2, mean2, rstd2 = K.layernorm_fwd(x2, sh["ln2w"], sh["ln2b"])
+        h, g = linear_fwd(ln2, sh["w1"], sh["b1"], epi=K.EPI_BF16_GELU)
+        x3 = linear_fwd(g, sh["w2"], sh["b2"], epi=K.EPI_BF16_RESIDUAL, aux=x2)
         saved += [mean2, rstd2, ln2, h, g]
         if kv_len is not None:
             saved.append(kv_len)
@@ -412,6 +440,8 @@ class _BlockFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dx3):
         blk, sh = ctx.blk, ctx.sh
+        if not _is_master(blk.attn.query.weight):
+            sh = blk._shadows()      # FSDP frees and re-gathers the unsharded parameters between forward and backward
         B, T, Ta, H, d, causal, cross, has_len = ctx.dims
         sv = list(ctx.saved_tensors)
         kv_len = sv.pop() if has_len else None
@@ -449,7 +479,7 @@ class _BlockFn(torch.autograd.Function):
         grads["mlp.0.bias"] = bg("mlp.0.bias", dh)
         dln2 = linear_dgrad(dh, sh["w1"])
         grads["mlp_ln.weight"], grads["mlp_ln.bias"] = vec("mlp_ln.weight"), vec("mlp_ln.bias")
-        dx2 = K.layernorm_bwd(dln2, x2, blk.mlp_ln.weight, mean2, rstd2, grads["mlp_ln.weight"], grads["mlp_ln.bias"],
+        dx2 = K.layernorm_bwd(dln2, x2, sh["ln2w"], mean2, rstd2, grads["mlp_ln.weight"], grads["mlp_ln.bias"],
                               dresidual=dx3)
         dxa = None
         if cross:
@@ -472,7 +502,7 @@ class _BlockFn(torch.autograd.Function):
             side.run(lambda: linear_dgrad(dkvc, sh["wckv"], out=dxa))
             dlnc = linear_dgrad(dqc, sh["wcq"])
             grads["cross_attn_ln.weight"], grads["cross_attn_ln.bias"] = vec("cross_attn_ln.weight"), vec("cross_attn_ln.bias")
-            dx1 = K.layernorm_bwd(dlnc, x1, blk.cross_attn_ln.weight, meanc, rstdc, grads["cross_attn_ln.weight"],
+            dx1 = K.layernorm_bwd(dlnc, x1, sh["lncw"], meanc, rstdc, grads["cross_attn_ln.weight"],
                                   grads["cross_attn_ln.bias"], dresidual=dx2)
         else:
             dx1 = dx2
@@ -493,7 +523,7 @@ class _BlockFn(torch.autograd.Function):
             bias_grad(dqkv[:, 2 * d:], d, side=side, out=D["attn.value.bias"])
         dln1 = linear_dgrad(dqkv, sh["wqkv"])
         grads["attn_ln.weight"], grads["attn_ln.bias"] = vec("attn_ln.weight"), vec("attn_ln.bias")
-        dx = K.layernorm_bwd(dln1, x, blk.attn_ln.weight, mean1, rstd1, grads["attn_ln.weight"], grads["attn_ln.bias"],
+        dx = K.layernorm_bwd(dln1, x, sh["ln1w"], mean1, rstd1, grads["attn_ln.weight"], grads["attn_ln.bias"],
                              dresidual=dx1)
         side.join()
         if D is not None:
@@ -523,24 +553,31 @@ class ResidualAttentionBlock(nn.Module):
         self._direct: Optional[Dict[str, Tensor]] = None
         self._bwd_done_cb = None
 
-    def _shadows(self):
+    def _build_shadows(self) -> Dict[str, Tensor]:
+        """Every operand the fused block kernels read that derives from a parameter: bf16 weights (fused where the GEMMs are
+        fused) and fp32 vectors (biases, LayerNorm affine)."""
+        a, c = self.attn, self.cross_attn
+        sh: Dict[str, Tensor] = {}
+        sh["wqkv"], sh["bqkv"] = a.fused_qkv()
+        sh["wo"], sh["bo"] = a.out.weight_bf16(), _f32(a.out.bias)
+        sh["ln1w"], sh["ln1b"] = _f32(self.attn_ln.weight), _f32(self.attn_ln.bias)
+        if c is not None:
+            sh["wcq"], sh["bcq"] = c.query.weight_bf16(), _f32(c.query.bias)
+            sh["wckv"], sh["bckv"] = c.fused_kv()
+            sh["wco"], sh["bco"] = c.out.weight_bf16(), _f32(c.out.bias)
+            sh["lncw"], sh["lncb"] = _f32(self.cross_attn_ln.weight), _f32(self.cross_attn_ln.bias)
+        sh["w1"], sh["b1"] = self.mlp[0].weight_bf16(), _f32(self.mlp[0].bias)
+        sh["w2"], sh["b2"] = self.mlp[2].weight_bf16(), _f32(self.mlp[2].bias)
+        sh["ln2w"], sh["ln2b"] = _f32(self.mlp_ln.weight), _f32(self.mlp_ln.bias)
+        return sh
+
+    def _shadows(self) -> Dict[str, Tensor]:
         if self._slab_sh is not None:
             return self._slab_sh
-        params = [p for _, p in self.named_parameters()]
-
-        def build():
-            sh = {}
-            sh["wqkv"], sh["bqkv"] = self.attn.fused_qkv()
-            sh["wo"] = self.attn.out.weight_bf16()
-            if self.cross_attn is not None:
-                sh["wcq"] = self.cross_attn.query.weight_bf16()
-                sh["wckv"], sh["bckv"] = self.cross_attn.fused_kv()
-                sh["wco"] = self.cross_attn.out.weight_bf16()
-            sh["w1"] = self.mlp[0].weight_bf16()
-            sh["w2"] = self.mlp[2].weight_bf16()
-            return sh
-
-        return self._shadow.get(params, build)
+        if not _is_master(self.attn.query.weight):
+            with torch.no_grad():
+                return self._build_shadows()        # FSDP mixed precision: parameters are transient views, never cached
+        return self._shadow.get([p for _, p in self.named_parameters()], self._build_shadows)
 
     def forward(self, x: Tensor, xa: Optional[Tensor] = None, mask: Optional[Tensor] = None,
                 kv_cache: Optional[dict] = None, verbose: bool = False):
@@ -564,8 +601,8 @@ class ResidualAttentionBlock(nn.Module):
         x = x + self.attn(self.attn_ln(x), mask=mask, kv_cache=kv_cache)[0]
         if self.cross_attn is not None:
             x = x + self.cross_attn(self.cross_attn_ln(x), xa, kv_cache=kv_cache)[0]
-        h, g = linear_fwd(_as_bf16_2d(self.mlp_ln(x)), self.mlp[0].weight_bf16(), self.mlp[0].bias, epi=K.EPI_BF16_GELU)
-        y = linear_fwd(g, self.mlp[2].weight_bf16(), self.mlp[2].bias, epi=K.EPI_BF16_RESIDUAL, aux=_as_bf16_2d(x))
+        h, g = linear_fwd(_as_bf16_2d(self.mlp_ln(x)), self.mlp[0].weight_bf16(), _f32(self.mlp[0].bias), epi=K.EPI_BF16_GELU)
+        y = linear_fwd(g, self.mlp[2].weight_bf16(), _f32(self.mlp[2].bias), epi=K.EPI_BF16_RESIDUAL, aux=_as_bf16_2d(x))
         return y.view(B, T, d)
 
 
@@ -582,10 +619,10 @@ class _StemFn(torch.autograd.Function):
         d = w1.shape[0]
         T2 = (T + 2 - 3) // 2 + 1
         A1 = K.im2col_conv1(mel.contiguous().float(), 3 * C)
-        pre1, h1 = linear_fwd(A1, enc.conv1.weight_bf16(), b1, epi=K.EPI_BF16_GELU)
+        pre1, h1 = linear_fwd(A1, enc.conv1.weight_bf16(), _f32(b1), epi=K.EPI_BF16_GELU)
         A2 = K.im2col_conv2(h1, B, T, d)
-        pre2, h2 = linear_fwd(A2, enc.conv2.weight_bf16(), b2, epi=K.EPI_BF16_GELU)
-        x0 = K.add_pos(h2, enc.positional_embedding, T2)
+        pre2, h2 = linear_fwd(A2, enc.conv2.weight_bf16(), _f32(b2), epi=K.EPI_BF16_GELU)
+        x0 = K.add_pos(h2, _f32(enc.positional_embedding), T2)
         ctx.save_for_backward(A1, pre1, A2, pre2)
         ctx.enc, ctx.dims = enc, (B, C, T, T2, d)
         return x0
@@ -646,7 +683,7 @@ class _LayerNormFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w, b, eps, owner=None, key=None):
-        y, mean, rstd = K.layernorm_fwd(x, w, b, eps)
+        y, mean, rstd = K.layernorm_fwd(x, _f32(w), _f32(b), eps)
         ctx.save_for_backward(x, w, mean, rstd)
         ctx.owner, ctx.key = owner, key
         return y
@@ -654,13 +691,14 @@ class _LayerNormFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, w, mean, rstd = ctx.saved_tensors
+        w = _f32(w)
         owner = ctx.owner
         D = owner._direct if (owner is not None and owner._direct is not None and owner._slabs.direct_grads) else None
         if D is not None:
             dx = K.layernorm_bwd(dy.contiguous(), x, w, mean, rstd, D[ctx.key + ".weight"], D[ctx.key + ".bias"])
             return dx, None, None, None, None, None
-        dw = torch.zeros_like(w)
-        db = torch.zeros_like(w)
+        dw = torch.zeros(w.shape, device=w.device, dtype=torch.float32)
+        db = torch.zeros(w.shape, device=w.device, dtype=torch.float32)
         dx = K.layernorm_bwd(dy.contiguous(), x, w, mean, rstd, dw, db)
         return dx, dw, db, None, None, None
 
@@ -673,7 +711,7 @@ class _EmbedFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, ids, emb, pos, offset, padding_idx, dec=None):
-        out = K.embed_fwd(ids.contiguous(), emb, pos, offset)
+        out = K.embed_fwd(ids.contiguous(), _f32(emb), _f32(pos), offset)
         ctx.save_for_backward(ids)
         ctx.meta = (emb.shape, pos.shape, offset, padding_idx)
         ctx.dec = dec
@@ -798,6 +836,8 @@ class TextDecoder(nn.Module):
         if self._emb_slab_view is not None:
             return self._emb_slab_view
         w = self.token_embedding.weight
+        if w.dtype == torch.bfloat16:
+            return w.detach()
         return self._emb_shadow.get((w,), lambda: K.cast_bf16(w.detach().contiguous()))
 
     def hidden(self, x: Tensor, xa: Tensor, kv_cache: Optional[dict] = None, padding_mask: Optional[Tensor] = None) -> Tensor:
@@ -909,14 +949,7 @@ class OLMoASRBase(nn.Module):
             for name, ln in (("attn_ln", b.attn_ln), ("cross_attn_ln", b.cross_attn_ln), ("mlp_ln", b.mlp_ln)):
                 if ln is not None:
                     direct[name + ".weight"], direct[name + ".bias"] = sl.grad(ln.weight), sl.grad(ln.bias)
-            sh = {}
-            sh["wqkv"], sh["bqkv"] = b.attn.fused_qkv()
-            sh["wo"] = b.attn.out.weight_bf16()
-            if b.cross_attn is not None:
-                sh["wcq"] = b.cross_attn.query.weight_bf16()
-                sh["wckv"], sh["bckv"] = b.cross_attn.fused_kv()
-                sh["wco"] = b.cross_attn.out.weight_bf16()
-            sh["w1"], sh["w2"] = b.mlp[0].weight_bf16(), b.mlp[2].weight_bf16()
+            sh = b._build_shadows()      # slab views throughout: bf16 weights from S, fp32 vectors from P
             b._slabs, b._slab_sh, b._direct = sl, sh, direct
         enc._slabs, dec._slabs = sl, sl
         enc._direct = {"conv1.weight": sl.grad(enc.conv1.weight), "conv1.bias": sl.grad(enc.conv1.bias),

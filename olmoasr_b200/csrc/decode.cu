@@ -521,6 +521,8 @@ extern "C" int oasr_convert(const void* src, int src_dtype, void* dst, int dst_d
   else if (src_dtype == OASR_DTYPE_F32 && dst_dtype == OASR_DTYPE_BF16) convert_kernel<float, bf16><<<blocks, 256, 0, st>>>((const float*)src, (bf16*)dst, n);
   else if (src_dtype == OASR_DTYPE_BF16 && dst_dtype == OASR_DTYPE_F16) convert_kernel<bf16, __half><<<blocks, 256, 0, st>>>((const bf16*)src, (__half*)dst, n);
   else if (src_dtype == OASR_DTYPE_F16 && dst_dtype == OASR_DTYPE_BF16) convert_kernel<__half, bf16><<<blocks, 256, 0, st>>>((const __half*)src, (bf16*)dst, n);
+  else if (src_dtype == OASR_DTYPE_BF16 && dst_dtype == OASR_DTYPE_F32) convert_kernel<bf16, float><<<blocks, 256, 0, st>>>((const bf16*)src, (float*)dst, n);
+  else if (src_dtype == OASR_DTYPE_F16 && dst_dtype == OASR_DTYPE_F32) convert_kernel<__half, float><<<blocks, 256, 0, st>>>((const __half*)src, (float*)dst, n);
   else OASR_REQUIRE(false, "convert: unsupported dtype pair %d -> %d", src_dtype, dst_dtype);
   OASR_LAUNCH_CHECK();
   return OASR_OK;

@@ -255,3 +255,16 @@ def colsum_(dy, db, N=None):
     N = dy.shape[1] if N is None else N
     call("oasr_colsum_bf16", ptr(dy), ptr(db), M, N, dy.stride(0), stream())
     return db
+
+
+_DTYPE_CODE = {torch.bfloat16: _lib.DTYPE_BF16, torch.float16: _lib.DTYPE_F16, torch.float32: _lib.DTYPE_F32}
+
+
+def convert(src, dst=None, dtype=None):
+    """Elementwise dtype conversion between contiguous tensors (f32 / bf16 / f16), round-to-nearest-even."""
+    _req(src.is_cuda and src.is_contiguous(), "convert: contiguous CUDA tensor")
+    if dst is None:
+        dst = torch.empty(src.shape, device=src.device, dtype=dtype)
+    _req(dst.is_contiguous() and dst.numel() == src.numel(), "convert: dst must be contiguous with the same number of elements")
+    call("oasr_convert", ptr(src), _DTYPE_CODE[src.dtype], ptr(dst), _DTYPE_CODE[dst.dtype], src.numel(), stream())
+    return dst
