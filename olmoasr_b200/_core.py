@@ -317,6 +317,13 @@ def _is_master(p: Tensor) -> bool:
     return p.dtype == torch.float32
 
 
+def _attr_by_path(mod: nn.Module, path: str) -> Tensor:
+    obj = mod
+    for part in path.split("."):
+        obj = getattr(obj, part)
+    return obj
+
+
 class MultiHeadAttention(nn.Module):
     """olmoasr/model.py:233-442.  `double_init` reproduces the training model's second kaiming draw (model.py:258-264)
     so that seeds give the reference's weights; the inference model draws once (inf_model.py:131-138)."""
@@ -591,7 +598,8 @@ class ResidualAttentionBlock(nn.Module):
                 kv_len = kv_len_from_padding_mask(mask)
         Ta = xa.shape[1] if xa is not None else 0
         xa2 = _as_bf16_2d(xa) if xa is not None else None
-        params = [self.get_parameter(n) for n in self._param_names]
+        # attribute walk, not get_parameter(): under FSDP the attributes are plain tensor views of the flat parameter
+        params = [_attr_by_path(self, n) for n in self._param_names]
         y = _BlockFn.apply(self, B, T, Ta, causal, kv_len, _as_bf16_2d(x), xa2, *params)
         return y.view(B, T, d)
 
