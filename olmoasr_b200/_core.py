@@ -197,7 +197,8 @@ def kv_len_from_padding_mask(padding_mask: Tensor) -> Tensor:
     cached = getattr(padding_mask, "_oasr_kv_len", None)   # computed once per decoder call, not once per block
     if cached is not None and cached[0] == padding_mask._version:
         return cached[1]
-    if padding_mask.dim() != 3 or padding_mask.shape[1] != padding_mask.shape[2] or padding_mask.dtype != torch.float32:
+    if padding_mask.dim() != 3 or padding_mask.shape[1] != padding_mask.shape[2] or \
+            padding_mask.dtype not in (torch.float32, torch.bfloat16, torch.float16):
         raise ValueError(f"padding_mask must be (B, n_ctx, n_ctx) float32, got {tuple(padding_mask.shape)} {padding_mask.dtype}")
     if not padding_mask.is_cuda:
         from ._lib import OasrError
@@ -208,7 +209,10 @@ def kv_len_from_padding_mask(padding_mask: Tensor) -> Tensor:
     if idx not in _mask_err:
         _mask_err[idx] = (torch.zeros(1, device=dev, dtype=torch.int32), torch.zeros(1, dtype=torch.int32).pin_memory(), None)
     flag, host, _ = _mask_err[idx]
-    kv = K.mask_to_kvlen(padding_mask.contiguous(), flag)
+    mask32 = padding_mask.contiguous()
+    if mask32.dtype != torch.float32:     # FSDP MixedPrecision casts the root module's floating-point inputs to bf16 (0 / -inf survive)
+        mask32 = K.convert(mask32, dtype=torch.float32)
+    kv = K.mask_to_kvlen(mask32, flag)
     host.copy_(flag, non_blocking=True)
     ev = torch.cuda.Event()
     ev.record()
@@ -626,7 +630,10 @@ class _StemFn(torch.autograd.Function):
         B, C, T = mel.shape
         d = w1.shape[0]
         T2 = (T + 2 - 3) // 2 + 1
-        A1 = K.im2col_conv1(mel.contiguous().float(), 3 * C)
+        mel = mel.contiguous()
+        if mel.dtype != torch.float32:        # FSDP MixedPrecision hands the root module a bf16 mel, as it does to the reference
+            mel = K.convert(mel, dtype=torch.float32)
+        A1 = K.im2col_conv1(mel, 3 * C)
         pre1, h1 = linear_fwd(A1, enc.conv1.weight_bf16(), _f32(b1), epi=K.EPI_BF16_GELU)
         A2 = K.im2col_conv2(h1, B, T, d)
         pre2, h2 = linear_fwd(A2, enc.conv2.weight_bf16(), _f32(b2), epi=K.EPI_BF16_GELU)

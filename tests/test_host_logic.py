@@ -66,6 +66,8 @@ def test_kv_len_accepts_lengths_and_rejects_what_it_cannot_derive():
     with pytest.raises(ValueError, match="padding_mask must be"):
         _core.kv_len_from_padding_mask(pm.double())
     with pytest.raises(OasrError, match="CUDA"):
+        _core.kv_len_from_padding_mask(pm.bfloat16())          # what FSDP's input cast produces: accepted (on the device)
+    with pytest.raises(OasrError, match="CUDA"):
         _core.kv_len_from_padding_mask(pm)                     # no CPU path
 
 
