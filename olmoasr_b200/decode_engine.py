@@ -200,8 +200,13 @@ class DecodeEngine:
         key = (n, self._sample_cfg)
         g = self._graphs.get(key)
         if g is None:
-            # the capture itself does not execute: state (pos, tokens) is untouched.  No warm-up run is needed because the
-            # kernels allocate nothing and the library has no lazily initialised state on this path.
+            # one eager run first (kernel modules are loaded lazily on first launch, which must not happen under capture),
+            # with the device-side decode state saved and restored around it; the capture itself does not execute
+            state = [t.clone() for t in (self.pos, self.tokens, self.sum_logprobs, self.no_speech, self.n_unfinished, self.done)]
+            self._enqueue_step(n)
+            torch.cuda.synchronize(self.dev)
+            for t, saved in zip((self.pos, self.tokens, self.sum_logprobs, self.no_speech, self.n_unfinished, self.done), state):
+                t.copy_(saved)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._enqueue_step(n)
