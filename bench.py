@@ -264,6 +264,7 @@ def our_arm(args):
         sync = SlabGradSync(model, slabs, bucket_bytes=int(os.environ.get("OASR_BUCKET_MB", "256")) << 20)
     elif world > 1:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], output_device=local_rank)
+        slabs.invalidate()      # DDP's constructor broadcast rank 0's weights into the masters behind autograd's back
     opt = FusedAdamW(model.parameters(), lr=1.5e-3, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.1, max_grad_norm=1.0, slabs=slabs)
 
     # synthetic batch of SURVEY.md 8(d); host copies are pinned (what a DataLoader with pin_memory hands over)

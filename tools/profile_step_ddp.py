@@ -27,8 +27,15 @@ def main():
     torch.manual_seed(0)
     with torch.device(dev):
         model = OLMoASR(ob.VARIANT_TO_DIMS["medium"])
-    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local])
-    opt = FusedAdamW(model.parameters())
+    impl = os.environ.get("OASR_DDP_IMPL", "slab")          # "slab": SlabGradSync (default); "torch": DistributedDataParallel
+    slabs = model.use_slabs(direct_grads=(impl == "slab"))
+    net, sync = model, None
+    if impl == "slab":
+        from olmoasr_b200.ddp import SlabGradSync
+        sync = SlabGradSync(model, slabs, bucket_bytes=int(os.environ.get("OASR_BUCKET_MB", "256")) << 20)
+    else:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local])
+    opt = FusedAdamW(model.parameters(), slabs=slabs)
     B = 32
     wav = synth.waveforms(B, int16=True).to(dev)
     ti, ty, pm, _ = (t.to(dev) for t in synth.text_batch(B))
@@ -36,9 +43,9 @@ def main():
     def step():
         mel = ob.log_mel_spectrogram(wav)
         loss = net(mel, ti, pm, targets=ty)
-        opt.zero_grad(set_to_none=True)
+        opt.zero_grad()
         loss.backward()
-        opt.step()
+        opt.step(inv_scale=sync.finish() if sync is not None else 1.0)
 
     for _ in range(3):
         step()
@@ -51,7 +58,8 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     if rank == 0:
-        print(f"# DDP x{dist.get_world_size()}: {e0.elapsed_time(e1) / 3:.2f} ms/step")
+        print(f"# data parallel x{dist.get_world_size()} ({impl}; segments {len(sync.segments) if sync else '-'}; NCCL_MAX_NCHANNELS="
+              f"{os.environ.get('NCCL_MAX_NCHANNELS', 'default')}): {e0.elapsed_time(e1) / 3:.2f} ms/step")
     from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         step()
