@@ -415,7 +415,8 @@ class _BlockFn(torch.autograd.Function):
     order.  Saves every GEMM input it needs for wgrad; recomputes nothing."""
 
     @staticmethod
-    def forward(ctx, blk, B, T, Ta, causal, kv_len, x, xa, *params):
+    def forward(ctx, blk, B, T, Ta, causal, kv_len, xa_state, x, xa, *params):
+        ctx.xa_state = xa_state
         H = blk.attn.n_head
         d = x.shape[1]
         sh = blk._shadows()
@@ -509,8 +510,25 @@ class _BlockFn(torch.autograd.Function):
                 grads["cross_attn.value.bias"] = bias_grad(dkvc, pool=pool, side=side)[d:]
             else:
                 bias_grad(dkvc[:, d:], d, side=side, out=D["cross_attn.value.bias"])
-            dxa = torch.empty_like(xa)   # only the encoder's backward reads it
-            side.run(lambda: linear_dgrad(dkvc, sh["wckv"], out=dxa))
+            # d(loss)/d(xa): every decoder layer contributes one (B*1500, d) term.  Instead of 24 separate tensors that
+            # autograd adds pairwise (23 elementwise kernels over 98 MB each at medium), the layers accumulate into ONE buffer
+            # through the GEMM's residual epilogue (bf16(buf + bf16(acc)), the rounding autograd's bf16 adds would apply);
+            # the layer whose backward runs last hands the sum to autograd.
+            st = ctx.xa_state
+            if st is None:
+                dxa = torch.empty_like(xa)
+                side.run(lambda: linear_dgrad(dkvc, sh["wckv"], out=dxa))
+            else:
+                first = st["buf"] is None
+                if first:
+                    st["buf"] = torch.empty_like(xa)
+                buf = st["buf"]
+                if first:
+                    side.run(lambda: linear_dgrad(dkvc, sh["wckv"], out=buf))
+                else:
+                    side.run(lambda: linear_dgrad(dkvc, sh["wckv"], epi=K.EPI_BF16_RESIDUAL, aux=buf, out=buf))
+                st["left"] -= 1
+                dxa = buf if st["left"] == 0 else None
             dlnc = linear_dgrad(dqc, sh["wcq"])
             grads["cross_attn_ln.weight"], grads["cross_attn_ln.bias"] = vec("cross_attn_ln.weight"), vec("cross_attn_ln.bias")
             dx1 = K.layernorm_bwd(dlnc, x1, sh["lncw"], meanc, rstdc, grads["cross_attn_ln.weight"],
@@ -540,8 +558,8 @@ class _BlockFn(torch.autograd.Function):
         if D is not None:
             if blk._bwd_done_cb is not None:
                 blk._bwd_done_cb()      # gradient synchronisation hook: this block's slab range is final
-            return (None, None, None, None, None, None, dx, dxa, *([None] * len(blk._param_names)))
-        return (None, None, None, None, None, None, dx, dxa, *[grads[n] for n in blk._param_names])
+            return (None, None, None, None, None, None, None, dx, dxa, *([None] * len(blk._param_names)))
+        return (None, None, None, None, None, None, None, dx, dxa, *[grads[n] for n in blk._param_names])
 
 
 class ResidualAttentionBlock(nn.Module):
@@ -591,7 +609,7 @@ class ResidualAttentionBlock(nn.Module):
         return self._shadow.get([p for _, p in self.named_parameters()], self._build_shadows)
 
     def forward(self, x: Tensor, xa: Optional[Tensor] = None, mask: Optional[Tensor] = None,
-                kv_cache: Optional[dict] = None, verbose: bool = False):
+                kv_cache: Optional[dict] = None, verbose: bool = False, _xa_state: Optional[dict] = None):
         if kv_cache is not None:
             return self._forward_cached(x, xa, mask, kv_cache)
         B, T, d = x.shape
@@ -604,7 +622,7 @@ class ResidualAttentionBlock(nn.Module):
         xa2 = _as_bf16_2d(xa) if xa is not None else None
         # attribute walk, not get_parameter(): under FSDP the attributes are plain tensor views of the flat parameter
         params = [_attr_by_path(self, n) for n in self._param_names]
-        y = _BlockFn.apply(self, B, T, Ta, causal, kv_len, _as_bf16_2d(x), xa2, *params)
+        y = _BlockFn.apply(self, B, T, Ta, causal, kv_len, _xa_state, _as_bf16_2d(x), xa2, *params)
         return y.view(B, T, d)
 
     def _forward_cached(self, x, xa, mask, kv_cache):
@@ -865,8 +883,11 @@ class TextDecoder(nn.Module):
         h = _EmbedFn.apply(x, self.token_embedding.weight, self.positional_embedding, offset,
                            self.token_embedding.padding_idx, self).view(B, S, d)
         mask = padding_mask if padding_mask is not None else self.mask[:S, :S]
+        # shared accumulator of the layers' gradients w.r.t. the encoder output (see _BlockFn.backward); one per forward pass
+        xa_state = {"buf": None, "left": len(self.blocks)} if (kv_cache is None and torch.is_grad_enabled() and xa.requires_grad) else None
         for block in self.blocks:
-            h = block(h, xa, mask=mask, kv_cache=kv_cache)
+            h = block(h, xa, mask=mask, kv_cache=kv_cache, _xa_state=xa_state) if xa_state is not None else \
+                block(h, xa, mask=mask, kv_cache=kv_cache)
         return _LayerNormFn.apply(h.reshape(B * S, d), self.ln.weight, self.ln.bias, self.ln.eps, self, "ln")
 
     def forward(self, x: Tensor, xa: Tensor, kv_cache: Optional[dict] = None, padding_mask: Optional[Tensor] = None,
