@@ -11,17 +11,29 @@ import torch
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 
 
+FLUSH = None
+
+
 def timeit(fn, iters=20):
+    """Per-call device time with the 126 MB L2 flushed before EVERY timed call (a 256 MB memset: round 1's version
+    allocated the flush buffer and never wrote it, so small inputs were served from L2 -- profiles/r01_membound_times.txt
+    shows >100 % lines).  Each call is bracketed by its own event pair; the flush is outside the pair."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    total = 0.0
+    pairs = []
     for _ in range(iters):
+        FLUSH.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         fn()
-    e1.record()
+        e1.record()
+        pairs.append((e0, e1))
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters
+    for e0, e1 in pairs:
+        total += e0.elapsed_time(e1)
+    return total / iters
 
 
 def main():
@@ -31,7 +43,8 @@ def main():
     hbm = json.loads(peaks.read_text())["hbm_gbs"] if peaks.exists() else 6500.0
     d = 1024
     g = torch.Generator(device=dev).manual_seed(0)
-    flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
+    global FLUSH
+    FLUSH = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
 
     def report(name, ms, nbytes):
         gbs = nbytes / ms / 1e6
@@ -53,8 +66,11 @@ def main():
             dbn = torch.zeros(n, device=dev)
             report(f"colsum         {rows}x{n}", timeit(lambda: K.colsum_(t, dbn)), rows * n * 2)
             del t
+    # log-mel at the bench's batch (32 clips, int16 in, fp32 out: 0.96 + 0.96 MB per clip)
+    from olmoasr_b200 import audio, synthetic
+    wav = synthetic.waveforms(32, int16=True).to(dev)
+    report("log_mel_spectrogram 32 x 480000 int16", timeit(lambda: audio.log_mel_spectrogram(wav)), 32 * (480000 * 2 + 80 * 3000 * 4))
     # fused optimizer at medium size is timed by the step profile (one launch per step)
-    del flush
 
 
 if __name__ == "__main__":
