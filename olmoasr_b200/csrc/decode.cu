@@ -24,6 +24,7 @@
 #include "common.cuh"
 
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace oasr {
 namespace {
@@ -63,12 +64,22 @@ template <typename T> __device__ __forceinline__ float rnd(float v) { return DT<
 
 __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
+// Programmatic dependent launch (a decode step is ~120 dependent launches of tiny kernels; at 1-8 sequences their launch
+// and first-byte latencies ARE the step time).  Every kernel lets its successor start launching at once
+// (launch_dependents) and blocks on wait() -- which returns when the predecessor grid has completed and flushed -- before
+// touching anything a predecessor writes.  What does not depend on a predecessor (the weight stream of dec_linear) is
+// issued BEFORE wait(), i.e. underneath the predecessor's tail.  Without the launch attribute both are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------------------------- embedding
 // x[n] = T(token_embedding[tokens[n, pos]] + positional_embedding[pos])   (inf_model.py:334-338; fp32 add, one rounding)
 template <typename T>
 __global__ void dec_embed_kernel(const int32_t* __restrict__ tokens, int64_t ld_tokens, const int32_t* __restrict__ pos_ptr,
                                  const float* __restrict__ emb, const float* __restrict__ pos_emb, T* __restrict__ x, int d,
                                  int n_vocab) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = blockIdx.x;
   const int pos = *pos_ptr;
   int tok = tokens[n * ld_tokens + pos];
@@ -120,6 +131,21 @@ __global__ void __launch_bounds__(256) dec_linear_kernel(const oasr_dec_linear_a
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int n0 = blockIdx.x * 16;
   const int K = a.K;
+  pdl_launch_dependents();
+  // the weight stream does not depend on the previous kernel: its first round is in flight before pdl_wait()
+  const T* W = static_cast<const T*>(a.W);
+  const int r0 = n0 + g, r1 = n0 + 8 + g;
+  const T* w0 = W + static_cast<int64_t>(r0 < a.N ? r0 : 0) * K + 8 * t;
+  const T* w1 = W + static_cast<int64_t>(r1 < a.N ? r1 : 0) * K + 8 * t;
+  const bool ok0 = r0 < a.N, ok1 = r1 < a.N;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  int k0 = warp * 32;
+  uint4 b0 = zero, b1 = zero;
+  if (k0 < K) {
+    b0 = ok0 ? __ldg(reinterpret_cast<const uint4*>(w0 + k0)) : zero;
+    b1 = ok1 ? __ldg(reinterpret_cast<const uint4*>(w1 + k0)) : zero;
+  }
+  pdl_wait();
   if (a.x_mode == X_LAYERNORM) {   // two-pass fp32 statistics per row (F.layer_norm(x.float()))
     for (int row = warp; row < a.M; row += 8) {
       const T* xr = static_cast<const T*>(a.x) + static_cast<int64_t>(row) * a.ldx;
@@ -151,33 +177,26 @@ __global__ void __launch_bounds__(256) dec_linear_kernel(const oasr_dec_linear_a
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
 
-  const T* W = static_cast<const T*>(a.W);
-  const int r0 = n0 + g, r1 = n0 + 8 + g;
-  const T* w0 = W + static_cast<int64_t>(r0 < a.N ? r0 : 0) * K + 8 * t;
-  const T* w1 = W + static_cast<int64_t>(r1 < a.N ? r1 : 0) * K + 8 * t;
-  const bool ok0 = r0 < a.N, ok1 = r1 < a.N;
-  const uint4 zero = make_uint4(0, 0, 0, 0);
-  int k0 = warp * 32;
-  uint4 b0 = zero, b1 = zero;
-  if (k0 < K) {
-    b0 = ok0 ? __ldg(reinterpret_cast<const uint4*>(w0 + k0)) : zero;
-    b1 = ok1 ? __ldg(reinterpret_cast<const uint4*>(w1 + k0)) : zero;
-  }
   for (; k0 < K; k0 += 256) {
     const int kn = k0 + 256;
     uint4 nb0 = zero, nb1 = zero;
-    if (kn < K) {   // the HBM stream runs one step ahead of the MMAs
+    if (kn < K) {   // the HBM stream runs one round ahead of the MMAs
       nb0 = ok0 ? __ldg(reinterpret_cast<const uint4*>(w0 + kn)) : zero;
       nb1 = ok1 ? __ldg(reinterpret_cast<const uint4*>(w1 + kn)) : zero;
     }
+    // all x fragments of this round first (2 MT independent L2 / L1 loads in flight), then the MMAs
+    uint4 xa[MT], xb[MT];
 #pragma unroll
     for (int i = 0; i < MT; ++i) {
-      const uint4 xa = load_x8<T>(a, s_stat, i * 16 + g, k0 + 8 * t);
-      const uint4 xb = load_x8<T>(a, s_stat, i * 16 + 8 + g, k0 + 8 * t);
-      DT<T>::mma(acc[i][0], xa.x, xb.x, xa.y, xb.y, b0.x, b0.y);
-      DT<T>::mma(acc[i][0], xa.z, xb.z, xa.w, xb.w, b0.z, b0.w);
-      DT<T>::mma(acc[i][1], xa.x, xb.x, xa.y, xb.y, b1.x, b1.y);
-      DT<T>::mma(acc[i][1], xa.z, xb.z, xa.w, xb.w, b1.z, b1.w);
+      xa[i] = load_x8<T>(a, s_stat, i * 16 + g, k0 + 8 * t);
+      xb[i] = load_x8<T>(a, s_stat, i * 16 + 8 + g, k0 + 8 * t);
+    }
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+      DT<T>::mma(acc[i][0], xa[i].x, xb[i].x, xa[i].y, xb[i].y, b0.x, b0.y);
+      DT<T>::mma(acc[i][0], xa[i].z, xb[i].z, xa[i].w, xb[i].w, b0.z, b0.w);
+      DT<T>::mma(acc[i][1], xa[i].x, xb[i].x, xa[i].y, xb[i].y, b1.x, b1.y);
+      DT<T>::mma(acc[i][1], xa[i].z, xb[i].z, xa[i].w, xb[i].w, b1.z, b1.w);
     }
     b0 = nb0; b1 = nb1;
   }
@@ -224,6 +243,8 @@ __global__ void __launch_bounds__(256) dec_linear_kernel(const oasr_dec_linear_a
 // grid (splits, H, N), 128 threads: 8 lanes per key row (16 bytes = 8 dims each), 16 keys per pass.
 template <typename T>
 __global__ void __launch_bounds__(128) dec_attn_scores_kernel(const oasr_dec_attn_args a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int s = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
   const int nkeys = a.pos_ptr ? (*a.pos_ptr + 1) : a.n_keys;
   const int per = (nkeys + gridDim.x - 1) / gridDim.x;
@@ -275,6 +296,8 @@ template <typename T>
 __global__ void __launch_bounds__(128) dec_attn_pv_kernel(const oasr_dec_attn_args a) {
   __shared__ float s_part[4];
   __shared__ float s_o[4][64];
+  pdl_launch_dependents();
+  pdl_wait();
   const int s = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
   const int nkeys = a.pos_ptr ? (*a.pos_ptr + 1) : a.n_keys;
   const int per = (nkeys + gridDim.x - 1) / gridDim.x;
@@ -338,6 +361,112 @@ __global__ void __launch_bounds__(128) dec_attn_pv_kernel(const oasr_dec_attn_ar
   }
 }
 
+// One CTA per (n, h) when the key range is not split (self-attention always; cross-attention once n x heads fills the
+// machine): scores stay in shared memory, softmax and P V follow in the same kernel -- one launch and no round trip through
+// global memory instead of two.  Same arithmetic and rounding points as the two-kernel form above.
+template <typename T>
+__global__ void __launch_bounds__(128) dec_attn_fused_kernel(const oasr_dec_attn_args a) {
+  __shared__ float s_sc[1536];
+  __shared__ float s_part[4];
+  __shared__ float s_o[4][64];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int h = blockIdx.y, n = blockIdx.z;
+  const int nkeys = a.pos_ptr ? (*a.pos_ptr + 1) : a.n_keys;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c8 = threadIdx.x & 7, slot = threadIdx.x >> 3;
+  const float scale = a.scale;
+  float qs[8];
+  {
+    const uint4 u = *reinterpret_cast<const uint4*>(static_cast<const T*>(a.q) + static_cast<int64_t>(n) * a.ldq + h * 64 + c8 * 8);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 p = DT<T>::unpack2(w[i]);
+      qs[2 * i] = rnd<T>(p.x * scale); qs[2 * i + 1] = rnd<T>(p.y * scale);
+    }
+  }
+  const T* kb = static_cast<const T*>(a.k) + static_cast<int64_t>(n) * a.kv_seq_stride + h * 64 + c8 * 8;
+  const T* vb = static_cast<const T*>(a.v) + static_cast<int64_t>(n) * a.kv_seq_stride + h * 64 + c8 * 8;
+  float m = -INFINITY;
+  for (int jb = 0; jb < nkeys; jb += 64) {
+    uint4 u[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int j = jb + r * 16 + slot;
+      u[r] = (j < nkeys) ? __ldg(reinterpret_cast<const uint4*>(kb + static_cast<int64_t>(j) * a.kv_row_stride)) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const uint32_t w[4] = {u[r].x, u[r].y, u[r].z, u[r].w};
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 p = DT<T>::unpack2(w[i]);
+        acc = fmaf(qs[2 * i], rnd<T>(p.x * scale), acc);
+        acc = fmaf(qs[2 * i + 1], rnd<T>(p.y * scale), acc);
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      const int j = jb + r * 16 + slot;
+      if (j < nkeys) {
+        const float sc = rnd<T>(acc);
+        if (c8 == 0) s_sc[j] = sc;
+        m = fmaxf(m, sc);
+      }
+    }
+  }
+  m = warp_max(m);
+  if (lane == 0) s_part[warp] = m;
+  __syncthreads();
+  m = fmaxf(fmaxf(s_part[0], s_part[1]), fmaxf(s_part[2], s_part[3]));
+  __syncthreads();
+  float l = 0.f;
+  for (int j = threadIdx.x; j < nkeys; j += 128) l += expf(s_sc[j] - m);
+  l = warp_sum(l);
+  if (lane == 0) s_part[warp] = l;
+  __syncthreads();
+  l = (s_part[0] + s_part[1]) + (s_part[2] + s_part[3]);
+  const float inv_l = 1.0f / l;
+  float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int jb = 0; jb < nkeys; jb += 64) {
+    uint4 u[4];
+    float p[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int j = jb + r * 16 + slot;
+      const bool ok = j < nkeys;
+      u[r] = ok ? __ldg(reinterpret_cast<const uint4*>(vb + static_cast<int64_t>(j) * a.kv_row_stride)) : make_uint4(0, 0, 0, 0);
+      p[r] = ok ? rnd<T>(expf(s_sc[j] - m) * inv_l) : 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const uint32_t w[4] = {u[r].x, u[r].y, u[r].z, u[r].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 vv = DT<T>::unpack2(w[i]);
+        o[2 * i] = fmaf(p[r], vv.x, o[2 * i]);
+        o[2 * i + 1] = fmaf(p[r], vv.y, o[2 * i + 1]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    o[i] += __shfl_xor_sync(0xffffffffu, o[i], 8);
+    o[i] += __shfl_xor_sync(0xffffffffu, o[i], 16);
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_o[warp][lane * 8 + i] = o[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int c = threadIdx.x;
+    a.out_partial[static_cast<int64_t>(n) * a.ld_out + h * 64 + c] = (s_o[0][c] + s_o[1][c]) + (s_o[2][c] + s_o[3][c]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------- sampling
 // One block per sequence over its fp32 logits row (whisper/decoding.py: SuppressBlank, SuppressTokens, GreedyDecoder.update):
 //   * at pos == sot_index: no_speech_prob = softmax(raw logits)[no_speech]                       (DecodingTask._main_loop)
@@ -349,6 +478,8 @@ __global__ void __launch_bounds__(256) dec_sample_kernel(const oasr_dec_sample_a
   __shared__ float s_f[8];
   __shared__ int s_i[8];
   __shared__ float s_bcast[2];
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = blockIdx.x;
   const int pos = *a.pos_ptr;
   const float* row = a.logits + static_cast<int64_t>(n) * a.ld_logits;
@@ -425,6 +556,8 @@ __global__ void __launch_bounds__(256) dec_sample_kernel(const oasr_dec_sample_a
 
 // pos += 1; done = (every sequence's last token is eot) -- the stop test of DecodingTask._main_loop, kept on the device
 __global__ void dec_advance_kernel(int32_t* pos_ptr, int32_t* n_unfinished, int32_t* done_flag, int sample_begin) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int pos = *pos_ptr;
   if (pos >= sample_begin - 1) *done_flag = (*n_unfinished == 0) ? 1 : 0;
   *n_unfinished = 0;
@@ -437,10 +570,29 @@ __global__ void convert_kernel(const TI* __restrict__ src, TO* __restrict__ dst,
     dst[i] = static_cast<TO>(static_cast<float>(src[i]));
 }
 
+// Launch with the programmatic-dependent-launch attribute (see pdl_wait above); OASR_DEC_PDL=0 launches plainly.
+inline bool pdl_enabled() {
+  static const int v = [] { const char* e = getenv("OASR_DEC_PDL"); return e ? atoi(e) : 1; }();
+  return v != 0;
+}
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 template <typename T, int MT>
 int launch_linear(const oasr_dec_linear_args& a, cudaStream_t st) {
-  dec_linear_kernel<T, MT><<<(unsigned)ceil_div(a.N, 16), 256, 0, st>>>(a);
-  OASR_LAUNCH_CHECK();
+  OASR_CUDA_OK(launch_pdl(dec_linear_kernel<T, MT>, dim3((unsigned)ceil_div(a.N, 16)), dim3(256), st, a));
   return OASR_OK;
 }
 template <typename T>
@@ -458,11 +610,13 @@ using namespace oasr;
 extern "C" int oasr_dec_embed(const int32_t* tokens, int64_t ld_tokens, const int32_t* pos_ptr, const float* emb, const float* pos_emb,
                               void* x, int64_t n_seq, int64_t d, int64_t n_vocab, int dtype, void* stream) {
   OASR_REQUIRE(n_seq > 0 && d > 0 && tokens && pos_ptr && emb && pos_emb && x, "dec_embed: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
   if (dtype == OASR_DTYPE_F16)
-    dec_embed_kernel<__half><<<(unsigned)n_seq, 128, 0, (cudaStream_t)stream>>>(tokens, ld_tokens, pos_ptr, emb, pos_emb, (__half*)x, (int)d, (int)n_vocab);
+    OASR_CUDA_OK(launch_pdl(dec_embed_kernel<__half>, dim3((unsigned)n_seq), dim3(128), st, tokens, ld_tokens, pos_ptr, emb, pos_emb,
+                            (__half*)x, (int)d, (int)n_vocab));
   else
-    dec_embed_kernel<bf16><<<(unsigned)n_seq, 128, 0, (cudaStream_t)stream>>>(tokens, ld_tokens, pos_ptr, emb, pos_emb, (bf16*)x, (int)d, (int)n_vocab);
-  OASR_LAUNCH_CHECK();
+    OASR_CUDA_OK(launch_pdl(dec_embed_kernel<bf16>, dim3((unsigned)n_seq), dim3(128), st, tokens, ld_tokens, pos_ptr, emb, pos_emb,
+                            (bf16*)x, (int)d, (int)n_vocab));
   return OASR_OK;
 }
 
@@ -490,16 +644,20 @@ extern "C" int oasr_dec_attention(const oasr_dec_attn_args* a, void* stream) {
   OASR_REQUIRE((a->ldq % 8) == 0 && (a->kv_row_stride % 8) == 0 && (a->kv_seq_stride % 8) == 0, "dec_attention: strides must be multiples of 8");
   dim3 grid((unsigned)a->n_splits, (unsigned)a->n_head, (unsigned)a->n_seq);
   cudaStream_t st = (cudaStream_t)stream;
-  if (a->dtype == OASR_DTYPE_F16) {
-    dec_attn_scores_kernel<__half><<<grid, 128, 0, st>>>(*a);
-    dec_attn_pv_kernel<__half><<<grid, 128, 0, st>>>(*a);
-  } else if (a->dtype == OASR_DTYPE_BF16) {
-    dec_attn_scores_kernel<bf16><<<grid, 128, 0, st>>>(*a);
-    dec_attn_pv_kernel<bf16><<<grid, 128, 0, st>>>(*a);
-  } else {
-    OASR_REQUIRE(false, "dec_attention: unknown dtype %d", a->dtype);
+  OASR_REQUIRE(a->dtype == OASR_DTYPE_F16 || a->dtype == OASR_DTYPE_BF16, "dec_attention: unknown dtype %d", a->dtype);
+  const bool f16 = a->dtype == OASR_DTYPE_F16;
+  if (a->n_splits == 1 && (a->pos_ptr != nullptr || a->n_keys <= 1536)) {   // whole key range in one CTA: fused form
+    if (f16) OASR_CUDA_OK(launch_pdl(dec_attn_fused_kernel<__half>, grid, dim3(128), st, *a));
+    else OASR_CUDA_OK(launch_pdl(dec_attn_fused_kernel<bf16>, grid, dim3(128), st, *a));
+    return OASR_OK;
   }
-  OASR_LAUNCH_CHECK();
+  if (f16) {
+    OASR_CUDA_OK(launch_pdl(dec_attn_scores_kernel<__half>, grid, dim3(128), st, *a));
+    OASR_CUDA_OK(launch_pdl(dec_attn_pv_kernel<__half>, grid, dim3(128), st, *a));
+  } else {
+    OASR_CUDA_OK(launch_pdl(dec_attn_scores_kernel<bf16>, grid, dim3(128), st, *a));
+    OASR_CUDA_OK(launch_pdl(dec_attn_pv_kernel<bf16>, grid, dim3(128), st, *a));
+  }
   return OASR_OK;
 }
 
@@ -507,9 +665,9 @@ extern "C" int oasr_dec_sample(const oasr_dec_sample_args* a, void* stream) {
   OASR_REQUIRE(a != nullptr && a->logits && a->tokens && a->pos_ptr && a->suppress && a->sum_logprobs && a->no_speech_prob &&
                    a->n_unfinished && a->done_flag, "dec_sample: null tensor");
   OASR_REQUIRE(a->n_seq >= 1 && a->n_vocab >= 1, "dec_sample: bad sizes");
-  dec_sample_kernel<<<(unsigned)a->n_seq, 256, 0, (cudaStream_t)stream>>>(*a);
-  dec_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(a->pos_ptr, a->n_unfinished, a->done_flag, a->sample_begin);
-  OASR_LAUNCH_CHECK();
+  OASR_CUDA_OK(launch_pdl(dec_sample_kernel, dim3((unsigned)a->n_seq), dim3(256), (cudaStream_t)stream, *a));
+  OASR_CUDA_OK(launch_pdl(dec_advance_kernel, dim3(1), dim3(1), (cudaStream_t)stream, a->pos_ptr, a->n_unfinished, a->done_flag,
+                          (int)a->sample_begin));
   return OASR_OK;
 }
 

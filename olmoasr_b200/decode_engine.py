@@ -12,7 +12,7 @@ What the reference does per step and what replaces it:
   * cross-attention K / V projected once, kept in the hook dict         -> projected once by the tcgen05 GEMM into a static
                                                                            (L, N*1500, 2d) buffer
   * 4 small matmul / softmax kernels per attention + separate LN, bias,
-    GELU, residual kernels                                               -> 10 launches per layer (csrc/decode.cu), 124 per step (small)
+    GELU, residual kernels                                               -> 8-9 launches per layer (csrc/decode.cu), 100-112 per step (small)
 
 The activation dtype is fp16 (upstream default `fp16=True`) or bf16; the decoder-step kernels reproduce the reference's
 rounding points in that dtype.  The audio encoder and the cross K/V projection run on the bf16 tcgen05 kernels in both
@@ -155,14 +155,16 @@ class DecodeEngine:
         a.n_keys = n_keys or 0
         a.n_seq, a.n_head, a.n_splits, a.scale, a.dtype = n, self.H, splits, 64 ** -0.25, self.dt
         call("oasr_dec_attention", ctypes.byref(a), stream())
+        if splits == 1:
+            _lib.LAUNCH_COUNT -= 1      # an unsplit key range runs as ONE fused kernel (scores + softmax + P V), not two
 
     def cross_splits(self, n: int) -> int:
         """Key-range splits of the cross-attention so that n x H x splits CTAs cover the 148 SMs twice (>= 94 keys each)."""
         return max(1, min(self.max_splits, math.ceil(2 * 148 / (n * self.H))))
 
     def _enqueue_step(self, n: int):
-        """One decoder step for sequences [0, n): 6 fused Linear launches + 2 x 2 attention launches per layer, plus the
-        embedding, the logits head and the 2 sampling launches."""
+        """One decoder step for sequences [0, n): per layer 6 fused Linear launches, 1 self-attention launch and 1 (unsplit key
+        range) or 2 (split) cross-attention launches; plus the embedding, the logits head and the 2 sampling launches."""
         w, d = self._w, self.d
         c0 = _lib.LAUNCH_COUNT
         call("oasr_dec_embed", ptr(self.tokens), self.tokens.stride(0), ptr(self.pos), ptr(w["emb"]), ptr(w["pos"]), ptr(self.x),

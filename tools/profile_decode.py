@@ -72,7 +72,8 @@ def main():
         # one step in launch order (the last replay): embed, then per layer LN+qkv, self scores, self pv, out, LN+q, cross scores,
         # cross pv, out, LN+fc1+GELU, fc2, ... , LN+logits, sample, advance
         last = sorted(evs, key=lambda ev: ev.time_range.start)[-eng.launches_per_step:]
-        names = ["embed"] + [f"L{l}.{k}" for l in range(eng.L) for k in ("qkv", "s_sc", "s_pv", "out", "cq", "c_sc", "c_pv", "cout", "fc1", "fc2")] + \
+        cross = ("c_att",) if eng.cross_splits(n) == 1 else ("c_sc", "c_pv")
+        names = ["embed"] + [f"L{l}.{k}" for l in range(eng.L) for k in ("qkv", "s_att", "out", "cq") + cross + ("cout", "fc1", "fc2")] + \
                 ["logits", "sample", "advance"]
         per = defaultdict(float)
         for nm, ev in zip(names, last):
