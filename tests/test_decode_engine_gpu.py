@@ -264,9 +264,16 @@ def test_skinny_linear_modes(dtype, M):
     lin(M, parts, W, b, out, x_mode=X_PARTIAL_SUM, n_partials=3)
     want = rT(rT(parts.sum(0)) @ W.float().t() + rT(b))
     assert float((out.float() - want).norm() / want.norm()) <= (2e-3 if dtype == torch.float16 else 1.5e-2)
-    # K = 3072 (fc2) with several k-rounds per warp
+    # K = 3072 (fc2): several k rounds per warp through the prefetch ring; at 64 rows the x tile is staged in K chunks
     x4 = torch.randn(M, 3072, device="cuda").to(dtype)
     W4 = (torch.randn(N, 3072, device="cuda") / math.sqrt(3072)).to(dtype)
     lin(M, x4, W4, b, out)
     want = rT(x4.float() @ W4.float().t() + rT(b))
     assert torch.allclose(out.float(), want, **tol)
+    # a wide output (like the 51864-column logits head): several 16-column groups per CTA, LayerNorm prologue staged once
+    Nw = 16 * 700 + 5
+    Ww = (torch.randn(Nw, Kd, device="cuda") / math.sqrt(Kd)).to(dtype)
+    lgw = torch.zeros(M, Nw, device="cuda")
+    lin(M, x, Ww, None, lgw, x_mode=X_LAYERNORM, ln=(gam, bet, 1e-5), epi=EPI_LOGITS_F32)
+    want = rT(xn @ Ww.float().t())
+    assert float((lgw - want).norm() / want.norm()) <= (2e-3 if dtype == torch.float16 else 1.5e-2)
