@@ -32,7 +32,9 @@ def wrap(model, local_rank, act_ckpt=True):
     fs = FSDP(model, device_id=local_rank, auto_wrap_policy=policy, mixed_precision=mp, backward_prefetch=BackwardPrefetch.BACKWARD_PRE,
               sharding_strategy=ShardingStrategy.FULL_SHARD)
     if act_ckpt:
-        apply_activation_checkpointing(fs, checkpoint_wrapper_fn=functools.partial(checkpoint_wrapper, offload_to_cpu=False,
+        # (the reference also passes offload_to_cpu=False, an argument torch >= 2.1 no longer has: it would be forwarded
+        # into ResidualAttentionBlock.forward)
+        apply_activation_checkpointing(fs, checkpoint_wrapper_fn=functools.partial(checkpoint_wrapper,
                                                                                   checkpoint_impl=CheckpointImpl.NO_REENTRANT),
                                        check_fn=lambda m: isinstance(m, ResidualAttentionBlock))
     return fs
