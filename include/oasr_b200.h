@@ -230,12 +230,15 @@ OASR_API int oasr_dec_attention(const oasr_dec_attn_args* args, void* stream);
 /* Logit filters + greedy choice + bookkeeping (whisper/decoding.py SuppressBlank, SuppressTokens, GreedyDecoder.update,
  * the no-speech probability and the stop test of DecodingTask._main_loop), then *pos += 1.
  * tokens: (n_seq, ld_tokens) int32, position *pos holds the token just fed; the choice is written to *pos + 1 once
- * *pos >= sample_begin - 1.  done_flag[0] = 1 when every sequence's newest token is eot. */
+ * *pos >= sample_begin - 1.  done_flag[0] = 1 when every sequence's newest token is eot.
+ * Each row is scanned by n_slices blocks (1..64); scratch: (n_seq, n_slices, 8) f32; counters: (n_seq,) int32, zero on
+ * entry and left zero (the block that arrives last merges the slices in slice order). */
 typedef struct oasr_dec_sample_args {
   const float* logits; int64_t ld_logits; int32_t* tokens; int64_t ld_tokens; int32_t* pos_ptr;
   const uint8_t* suppress; float* sum_logprobs; float* no_speech_prob; int32_t* n_unfinished; int32_t* done_flag;
+  float* scratch; int32_t* counters;
   int32_t n_seq; int32_t n_vocab; int32_t sample_begin; int32_t sot_index; int32_t suppress_blank; int32_t blank;
-  int32_t eot; int32_t no_speech;
+  int32_t eot; int32_t no_speech; int32_t n_slices; int32_t reserved;
 } oasr_dec_sample_args;
 OASR_API int oasr_dec_sample(const oasr_dec_sample_args* args, void* stream);
 

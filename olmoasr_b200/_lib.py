@@ -52,9 +52,9 @@ class DecAttnArgs(ctypes.Structure):  # oasr_dec_attn_args
 class DecSampleArgs(ctypes.Structure):  # oasr_dec_sample_args
     _fields_ = [("logits", c_void_p), ("ld_logits", c_i64), ("tokens", c_void_p), ("ld_tokens", c_i64), ("pos_ptr", c_void_p),
                 ("suppress", c_void_p), ("sum_logprobs", c_void_p), ("no_speech_prob", c_void_p), ("n_unfinished", c_void_p),
-                ("done_flag", c_void_p),
+                ("done_flag", c_void_p), ("scratch", c_void_p), ("counters", c_void_p),
                 ("n_seq", c_i32), ("n_vocab", c_i32), ("sample_begin", c_i32), ("sot_index", c_i32), ("suppress_blank", c_i32),
-                ("blank", c_i32), ("eot", c_i32), ("no_speech", c_i32)]
+                ("blank", c_i32), ("eot", c_i32), ("no_speech", c_i32), ("n_slices", c_i32), ("reserved", c_i32)]
 
 
 # name -> argtypes (restype is always int unless listed in _RESTYPES)

@@ -108,46 +108,70 @@ enum { EPI_STORE = 0, EPI_GELU = 1, EPI_RESIDUAL = 2, EPI_LOGITS_F32 = 3, EPI_QK
 constexpr int DEC_PF = 4;        // W rounds in flight per warp
 constexpr int DEC_XPAD = 32;     // elements of row padding in the staged x tile
 
-template <typename T>
-__device__ __forceinline__ void stage_row_layernorm(const oasr_dec_linear_args& a, int row, int lane, T* dst) {
-  // one warp, one row: the row lives in registers between the mean, the variance and the normalisation (two-pass fp32
-  // statistics like F.layer_norm(x.float()), one rounding to T: inf_model.py LayerNorm)
+template <typename T, int R>
+__device__ __forceinline__ void stage_rows_layernorm(const oasr_dec_linear_args& a, int row0, int row_step, int lane, T* x_s, int lds) {
+  // one warp, R rows (row0, row0 + row_step, ...): each row lives in registers between the mean, the variance and the
+  // normalisation (two-pass fp32 statistics like F.layer_norm(x.float()), one rounding to T: inf_model.py LayerNorm).
+  // Every global access -- the R rows, and L1 prefetches of the affine parameters -- is issued before the first reduction.
   const int K = a.K;
-  const T* xr = static_cast<const T*>(a.x) + static_cast<int64_t>(row) * a.ldx;
-  uint4 u[5];
-  float s = 0.f;
+  uint4 u[R][5];
 #pragma unroll
-  for (int i = 0; i < 5; ++i) {
-    const int k = (lane + 32 * i) * 8;
-    u[i] = (k < K) ? *reinterpret_cast<const uint4*>(xr + k) : make_uint4(0, 0, 0, 0);
-    const float2 p0 = DT<T>::unpack2(u[i].x), p1 = DT<T>::unpack2(u[i].y), p2 = DT<T>::unpack2(u[i].z), p3 = DT<T>::unpack2(u[i].w);
-    s += (p0.x + p0.y) + (p1.x + p1.y) + (p2.x + p2.y) + (p3.x + p3.y);
-  }
-  const float mean = warp_sum(s) / static_cast<float>(K);
-  float q = 0.f;
+  for (int r = 0; r < R; ++r) {
+    const int row = row0 + r * row_step;
+    const T* xr = static_cast<const T*>(a.x) + static_cast<int64_t>(row < a.M ? row : 0) * a.ldx;
 #pragma unroll
-  for (int i = 0; i < 5; ++i) {
-    const int k = (lane + 32 * i) * 8;
-    if (k < K) {
-      const float2 p0 = DT<T>::unpack2(u[i].x), p1 = DT<T>::unpack2(u[i].y), p2 = DT<T>::unpack2(u[i].z), p3 = DT<T>::unpack2(u[i].w);
-      const float d0 = p0.x - mean, d1 = p0.y - mean, d2 = p1.x - mean, d3 = p1.y - mean;
-      const float d4 = p2.x - mean, d5 = p2.y - mean, d6 = p3.x - mean, d7 = p3.y - mean;
-      q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3) + (d4 * d4 + d5 * d5) + (d6 * d6 + d7 * d7);
+    for (int i = 0; i < 5; ++i) {
+      const int k = (lane + 32 * i) * 8;
+      u[r][i] = (k < K && row < a.M) ? *reinterpret_cast<const uint4*>(xr + k) : make_uint4(0, 0, 0, 0);
     }
   }
-  const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(K) + a.ln_eps);
 #pragma unroll
-  for (int i = 0; i < 5; ++i) {
+  for (int i = 0; i < 5; ++i) {      // the affine parameters this lane will need: pulled into L1 now, read (as hits) below
     const int k = (lane + 32 * i) * 8;
     if (k < K) {
-      const float4 g0 = *reinterpret_cast<const float4*>(a.ln_gamma + k), g1 = *reinterpret_cast<const float4*>(a.ln_gamma + k + 4);
-      const float4 b0 = *reinterpret_cast<const float4*>(a.ln_beta + k), b1 = *reinterpret_cast<const float4*>(a.ln_beta + k + 4);
-      const float2 x0 = DT<T>::unpack2(u[i].x), x1 = DT<T>::unpack2(u[i].y), x2 = DT<T>::unpack2(u[i].z), x3 = DT<T>::unpack2(u[i].w);
-      *reinterpret_cast<uint4*>(dst + k) =
-          make_uint4(DT<T>::pack2((x0.x - mean) * rstd * g0.x + b0.x, (x0.y - mean) * rstd * g0.y + b0.y),
-                     DT<T>::pack2((x1.x - mean) * rstd * g0.z + b0.z, (x1.y - mean) * rstd * g0.w + b0.w),
-                     DT<T>::pack2((x2.x - mean) * rstd * g1.x + b1.x, (x2.y - mean) * rstd * g1.y + b1.y),
-                     DT<T>::pack2((x3.x - mean) * rstd * g1.z + b1.z, (x3.y - mean) * rstd * g1.w + b1.w));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(a.ln_gamma + k));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(a.ln_beta + k));
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int row = row0 + r * row_step;
+    T* dst = x_s + static_cast<size_t>(row) * lds;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const float2 p0 = DT<T>::unpack2(u[r][i].x), p1 = DT<T>::unpack2(u[r][i].y), p2 = DT<T>::unpack2(u[r][i].z), p3 = DT<T>::unpack2(u[r][i].w);
+      s += (p0.x + p0.y) + (p1.x + p1.y) + (p2.x + p2.y) + (p3.x + p3.y);      // zero-filled beyond K
+    }
+    const float mean = warp_sum(s) / static_cast<float>(K);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int k = (lane + 32 * i) * 8;
+      if (k < K) {
+        const float2 p0 = DT<T>::unpack2(u[r][i].x), p1 = DT<T>::unpack2(u[r][i].y), p2 = DT<T>::unpack2(u[r][i].z), p3 = DT<T>::unpack2(u[r][i].w);
+        const float d0 = p0.x - mean, d1 = p0.y - mean, d2 = p1.x - mean, d3 = p1.y - mean;
+        const float d4 = p2.x - mean, d5 = p2.y - mean, d6 = p3.x - mean, d7 = p3.y - mean;
+        q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3) + (d4 * d4 + d5 * d5) + (d6 * d6 + d7 * d7);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(K) + a.ln_eps);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int k = (lane + 32 * i) * 8;
+      if (k < K) {
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (row < a.M) {
+          const float4 g0 = *reinterpret_cast<const float4*>(a.ln_gamma + k), g1 = *reinterpret_cast<const float4*>(a.ln_gamma + k + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(a.ln_beta + k), b1 = *reinterpret_cast<const float4*>(a.ln_beta + k + 4);
+          const float2 x0 = DT<T>::unpack2(u[r][i].x), x1 = DT<T>::unpack2(u[r][i].y), x2 = DT<T>::unpack2(u[r][i].z), x3 = DT<T>::unpack2(u[r][i].w);
+          o = make_uint4(DT<T>::pack2((x0.x - mean) * rstd * g0.x + b0.x, (x0.y - mean) * rstd * g0.y + b0.y),
+                         DT<T>::pack2((x1.x - mean) * rstd * g0.z + b0.z, (x1.y - mean) * rstd * g0.w + b0.w),
+                         DT<T>::pack2((x2.x - mean) * rstd * g1.x + b1.x, (x2.y - mean) * rstd * g1.y + b1.y),
+                         DT<T>::pack2((x3.x - mean) * rstd * g1.z + b1.z, (x3.y - mean) * rstd * g1.w + b1.w));
+        }
+        *reinterpret_cast<uint4*>(dst + k) = o;
+      }
     }
   }
 }
@@ -168,7 +192,7 @@ __device__ __forceinline__ uint4 load_x_plain_or_partial(const oasr_dec_linear_a
 }
 
 template <typename T, int MT>
-__global__ void __launch_bounds__(256) dec_linear_kernel(const oasr_dec_linear_args a, const int KC, const int groups) {
+__global__ void __launch_bounds__(256, (MT <= 2 ? 2 : 1)) dec_linear_kernel(const oasr_dec_linear_args a, const int KC, const int groups) {
   constexpr int MP = 16 * MT;
   extern __shared__ __align__(16) uint8_t dec_smem[];
   const int K = a.K;
@@ -206,17 +230,30 @@ __global__ void __launch_bounds__(256) dec_linear_kernel(const oasr_dec_linear_a
   auto stage = [&](int kc0) {     // x[:, kc0 : kc0 + KC) -> shared memory as T (rows >= M are zero)
     const int kc = min(KC, K - kc0);
     if (a.x_mode == X_LAYERNORM) {                       // whole rows (KC >= K is guaranteed by the host)
-      for (int row = warp; row < MP; row += 8) {
-        T* dst = x_s + static_cast<size_t>(row) * lds;
-        if (row < a.M) stage_row_layernorm<T>(a, row, lane, dst);
-        else for (int k = lane * 8; k < K; k += 256) *reinterpret_cast<uint4*>(dst + k) = zero;
+      // warp w owns rows w, w + 8, ...: MT of them, two at a time (all their loads in flight together)
+      if constexpr (MT == 1) {
+        stage_rows_layernorm<T, 2>(a, warp, 8, lane, x_s, lds);
+      } else {
+#pragma unroll 1
+        for (int i = 0; i < 2 * MT; i += 2) stage_rows_layernorm<T, 2>(a, warp + 8 * i, 8, lane, x_s, lds);
       }
     } else {
       const int vec = kc >> 3;
-      for (int idx = threadIdx.x; idx < MP * vec; idx += 256) {
-        const int row = idx / vec, v = idx - row * vec;
-        const uint4 val = (row < a.M) ? load_x_plain_or_partial<T>(a, row, kc0 + v * 8) : zero;
-        *reinterpret_cast<uint4*>(x_s + static_cast<size_t>(row) * lds + v * 8) = val;
+      const int items = MP * vec;
+      for (int idx0 = threadIdx.x; idx0 < items; idx0 += 256 * 4) {       // 4 independent loads in flight per thread
+        uint4 val[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int idx = idx0 + 256 * q;
+          const int row = idx / vec, v = idx - row * vec;
+          val[q] = (idx < items && row < a.M) ? load_x_plain_or_partial<T>(a, row, kc0 + v * 8) : zero;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int idx = idx0 + 256 * q;
+          const int row = idx / vec, v = idx - row * vec;
+          if (idx < items) *reinterpret_cast<uint4*>(x_s + static_cast<size_t>(row) * lds + v * 8) = val[q];
+        }
       }
     }
   };
@@ -345,15 +382,15 @@ __global__ void __launch_bounds__(128) dec_attn_scores_kernel(const oasr_dec_att
   }
   const T* kb = static_cast<const T*>(a.k) + static_cast<int64_t>(n) * a.kv_seq_stride + h * 64 + c8 * 8;
   float* out = a.scores + (static_cast<int64_t>(n) * gridDim.y + h) * a.scores_ld;
-  for (int jb = j0; jb < j1; jb += 64) {   // 4 independent 16-byte loads in flight per thread
-    uint4 u[4];
+  for (int jb = j0; jb < j1; jb += 128) {   // 8 independent 16-byte loads in flight per thread
+    uint4 u[8];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < 8; ++r) {
       const int j = jb + r * 16 + slot;
       u[r] = (j < j1) ? __ldg(reinterpret_cast<const uint4*>(kb + static_cast<int64_t>(j) * a.kv_row_stride)) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < 8; ++r) {
       const uint32_t w[4] = {u[r].x, u[r].y, u[r].z, u[r].w};
       float acc = 0.f;
 #pragma unroll
@@ -404,18 +441,18 @@ __global__ void __launch_bounds__(128) dec_attn_pv_kernel(const oasr_dec_attn_ar
   const int c8 = threadIdx.x & 7, slot = threadIdx.x >> 3;
   const T* vb = static_cast<const T*>(a.v) + static_cast<int64_t>(n) * a.kv_seq_stride + h * 64 + c8 * 8;
   float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int jb = j0; jb < j1; jb += 64) {
-    uint4 u[4];
-    float p[4];
+  for (int jb = j0; jb < j1; jb += 128) {
+    uint4 u[8];
+    float p[8];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < 8; ++r) {
       const int j = jb + r * 16 + slot;
       const bool ok = j < j1;
       u[r] = ok ? __ldg(reinterpret_cast<const uint4*>(vb + static_cast<int64_t>(j) * a.kv_row_stride)) : make_uint4(0, 0, 0, 0);
       p[r] = ok ? rnd<T>(expf(sc[j] - m) * inv_l) : 0.f;            // softmax(...).to(q.dtype)
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < 8; ++r) {
       const uint32_t w[4] = {u[r].x, u[r].y, u[r].z, u[r].w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -471,15 +508,15 @@ __global__ void __launch_bounds__(128) dec_attn_fused_kernel(const oasr_dec_attn
   const T* kb = static_cast<const T*>(a.k) + static_cast<int64_t>(n) * a.kv_seq_stride + h * 64 + c8 * 8;
   const T* vb = static_cast<const T*>(a.v) + static_cast<int64_t>(n) * a.kv_seq_stride + h * 64 + c8 * 8;
   float m = -INFINITY;
-  for (int jb = 0; jb < nkeys; jb += 64) {
-    uint4 u[4];
+  for (int jb = 0; jb < nkeys; jb += 128) {
+    uint4 u[8];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < 8; ++r) {
       const int j = jb + r * 16 + slot;
       u[r] = (j < nkeys) ? __ldg(reinterpret_cast<const uint4*>(kb + static_cast<int64_t>(j) * a.kv_row_stride)) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < 8; ++r) {
       const uint32_t w[4] = {u[r].x, u[r].y, u[r].z, u[r].w};
       float acc = 0.f;
 #pragma unroll
@@ -512,18 +549,18 @@ __global__ void __launch_bounds__(128) dec_attn_fused_kernel(const oasr_dec_attn
   l = (s_part[0] + s_part[1]) + (s_part[2] + s_part[3]);
   const float inv_l = 1.0f / l;
   float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int jb = 0; jb < nkeys; jb += 64) {
-    uint4 u[4];
-    float p[4];
+  for (int jb = 0; jb < nkeys; jb += 128) {
+    uint4 u[8];
+    float p[8];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < 8; ++r) {
       const int j = jb + r * 16 + slot;
       const bool ok = j < nkeys;
       u[r] = ok ? __ldg(reinterpret_cast<const uint4*>(vb + static_cast<int64_t>(j) * a.kv_row_stride)) : make_uint4(0, 0, 0, 0);
       p[r] = ok ? rnd<T>(expf(s_sc[j] - m) * inv_l) : 0.f;
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < 8; ++r) {
       const uint32_t w[4] = {u[r].x, u[r].y, u[r].z, u[r].w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -550,19 +587,42 @@ __global__ void __launch_bounds__(128) dec_attn_fused_kernel(const oasr_dec_attn
 }
 
 // ---------------------------------------------------------------------------------------------------------- sampling
-// One block per sequence over its fp32 logits row (whisper/decoding.py: SuppressBlank, SuppressTokens, GreedyDecoder.update):
+// `n_slices` blocks per sequence, each over a contiguous slice of its fp32 logits row, one online pass with 16-byte loads
+// (whisper/decoding.py: SuppressBlank, SuppressTokens, GreedyDecoder.update); the block that arrives last at the sequence's
+// counter merges the slices in slice order (deterministic) and does the bookkeeping:
 //   * at pos == sot_index: no_speech_prob = softmax(raw logits)[no_speech]                       (DecodingTask._main_loop)
 //   * suppress[v] != 0 -> -inf; at the first sampled position also `blank` and `eot`            (SuppressTokens / SuppressBlank)
 //   * next = argmax (lowest index on ties); logprob = logit[next] - logsumexp(filtered row)
 //   * sum_logprobs += logprob unless the previous token is eot; rows whose previous token is eot keep emitting eot
 // Positions before sample_begin - 1 are teacher-forced: nothing is written there.
+struct SampleAcc {          // online (max, sum exp) of the raw and the filtered row + filtered argmax
+  float mraw, sraw, mf, sf;
+  int arg;
+};
+__device__ __forceinline__ void acc_raw(SampleAcc& s, float x) {
+  if (x > s.mraw) { s.sraw = s.sraw * expf(s.mraw - x) + 1.f; s.mraw = x; }
+  else s.sraw += expf(x - s.mraw);
+}
+__device__ __forceinline__ void acc_filt(SampleAcc& s, float x, int v) {
+  if (x > s.mf) { s.sf = s.sf * expf(s.mf - x) + 1.f; s.mf = x; s.arg = v; }
+  else { s.sf += expf(x - s.mf); if (x == s.mf && v < s.arg) s.arg = v; }
+}
+__device__ __forceinline__ SampleAcc acc_merge(const SampleAcc& a, const SampleAcc& b) {
+  SampleAcc r;
+  r.mraw = fmaxf(a.mraw, b.mraw);
+  r.sraw = (r.mraw == -INFINITY) ? 0.f : a.sraw * expf(a.mraw - r.mraw) + b.sraw * expf(b.mraw - r.mraw);
+  r.mf = fmaxf(a.mf, b.mf);
+  r.sf = (r.mf == -INFINITY) ? 0.f : a.sf * expf(a.mf - r.mf) + b.sf * expf(b.mf - r.mf);
+  r.arg = (a.mf > b.mf || (a.mf == b.mf && a.arg < b.arg)) ? a.arg : b.arg;
+  return r;
+}
+
 __global__ void __launch_bounds__(256) dec_sample_kernel(const oasr_dec_sample_args a) {
-  __shared__ float s_f[8];
-  __shared__ int s_i[8];
-  __shared__ float s_bcast[2];
+  __shared__ SampleAcc s_acc[8];
+  __shared__ int s_last;
   pdl_launch_dependents();
   pdl_wait();
-  const int n = blockIdx.x;
+  const int slice = blockIdx.x, n = blockIdx.y, S = gridDim.x;
   const int pos = *a.pos_ptr;
   const float* row = a.logits + static_cast<int64_t>(n) * a.ld_logits;
   const int V = a.n_vocab;
@@ -572,67 +632,65 @@ __global__ void __launch_bounds__(256) dec_sample_kernel(const oasr_dec_sample_a
   const bool want_raw = (pos == a.sot_index);
   if (!sampling && !want_raw) return;
 
-  // pass 1: maxima (raw and filtered) and the filtered argmax
-  float mraw = -INFINITY, mf = -INFINITY;
-  int arg = V;
-  for (int v = threadIdx.x; v < V; v += 256) {
-    const float x = row[v];
-    mraw = fmaxf(mraw, x);
+  const int per = ((V + S - 1) / S + 3) & ~3;                  // slice length, a multiple of 4 (16-byte loads)
+  const int v0 = slice * per, v1 = min(V, v0 + per);
+  SampleAcc acc{-INFINITY, 0.f, -INFINITY, 0.f, V};
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
+  auto visit = [&](float x, int v) {
+    acc_raw(acc, x);
     const bool sup = a.suppress[v] != 0 || (first && a.suppress_blank && (v == a.blank || v == a.eot));
-    if (!sup && (x > mf || (x == mf && v < arg))) { mf = x; arg = v; }
-  }
-  for (int o = 16; o > 0; o >>= 1) {
-    const float om = __shfl_xor_sync(0xffffffffu, mf, o);
-    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
-    if (om > mf || (om == mf && oa < arg)) { mf = om; arg = oa; }
-    mraw = fmaxf(mraw, __shfl_xor_sync(0xffffffffu, mraw, o));
-  }
-  if (lane == 0) { s_f[warp] = mf; s_i[warp] = arg; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float bm = s_f[0]; int ba = s_i[0];
-    for (int w = 1; w < 8; ++w)
-      if (s_f[w] > bm || (s_f[w] == bm && s_i[w] < ba)) { bm = s_f[w]; ba = s_i[w]; }
-    s_bcast[0] = bm; s_i[0] = ba;
-  }
-  __syncthreads();
-  mf = s_bcast[0]; arg = s_i[0];
-  __syncthreads();
-  if (lane == 0) s_f[warp] = mraw;
-  __syncthreads();
-  mraw = fmaxf(fmaxf(fmaxf(s_f[0], s_f[1]), fmaxf(s_f[2], s_f[3])), fmaxf(fmaxf(s_f[4], s_f[5]), fmaxf(s_f[6], s_f[7])));
-  __syncthreads();
-
-  // pass 2: normalisers
-  float sraw = 0.f, sf = 0.f;
-  for (int v = threadIdx.x; v < V; v += 256) {
-    const float x = row[v];
-    sraw += expf(x - mraw);
-    const bool sup = a.suppress[v] != 0 || (first && a.suppress_blank && (v == a.blank || v == a.eot));
-    if (!sup) sf += expf(x - mf);
-  }
-  sraw = warp_sum(sraw); sf = warp_sum(sf);
-  if (lane == 0) { s_f[warp] = sf; }
-  __syncthreads();
-  float tf = 0.f;
-  for (int w = 0; w < 8; ++w) tf += s_f[w];
-  __syncthreads();
-  if (lane == 0) { s_f[warp] = sraw; }
-  __syncthreads();
-  float traw = 0.f;
-  for (int w = 0; w < 8; ++w) traw += s_f[w];
-
-  if (threadIdx.x == 0) {
-    if (want_raw) a.no_speech_prob[n] = expf(row[a.no_speech] - mraw) / traw;
-    if (sampling) {
-      const int prev = a.tokens[static_cast<int64_t>(n) * a.ld_tokens + pos];
-      const bool finished = (prev == a.eot);
-      const float logprob = -logf(tf);            // logit[arg] - (mf + log sum exp(x - mf)), logit[arg] == mf
-      if (!finished) a.sum_logprobs[n] += logprob;
-      const int next = finished ? a.eot : arg;
-      a.tokens[static_cast<int64_t>(n) * a.ld_tokens + pos + 1] = next;
-      if (next != a.eot) atomicAdd(a.n_unfinished, 1);
+    if (!sup) acc_filt(acc, x, v);
+  };
+  if (vec_ok) {
+    for (int v = v0 + threadIdx.x * 4; v < v1; v += 256 * 4) {
+      if (v + 4 <= v1) {
+        const float4 x = *reinterpret_cast<const float4*>(row + v);
+        visit(x.x, v); visit(x.y, v + 1); visit(x.z, v + 2); visit(x.w, v + 3);
+      } else {
+        for (int u = v; u < v1; ++u) visit(row[u], u);
+      }
     }
+  } else {
+    for (int v = v0 + threadIdx.x; v < v1; v += 256) visit(row[v], v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    SampleAcc other;
+    other.mraw = __shfl_xor_sync(0xffffffffu, acc.mraw, o); other.sraw = __shfl_xor_sync(0xffffffffu, acc.sraw, o);
+    other.mf = __shfl_xor_sync(0xffffffffu, acc.mf, o); other.sf = __shfl_xor_sync(0xffffffffu, acc.sf, o);
+    other.arg = __shfl_xor_sync(0xffffffffu, acc.arg, o);
+    acc = acc_merge(acc, other);
+  }
+  if (lane == 0) s_acc[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    SampleAcc t = s_acc[0];
+    for (int w = 1; w < 8; ++w) t = acc_merge(t, s_acc[w]);
+    float* out = a.scratch + (static_cast<int64_t>(n) * S + slice) * 8;
+    out[0] = t.mraw; out[1] = t.sraw; out[2] = t.mf; out[3] = t.sf; out[4] = __int_as_float(t.arg);
+    __threadfence();
+    s_last = (atomicAdd(a.counters + n, 1) == S - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  __threadfence();
+  SampleAcc t{-INFINITY, 0.f, -INFINITY, 0.f, V};
+  for (int sl = 0; sl < S; ++sl) {       // slice order: the result does not depend on which block arrived last
+    const volatile float* in = a.scratch + (static_cast<int64_t>(n) * S + sl) * 8;
+    SampleAcc p;
+    p.mraw = in[0]; p.sraw = in[1]; p.mf = in[2]; p.sf = in[3]; p.arg = __float_as_int(in[4]);
+    t = acc_merge(t, p);
+  }
+  a.counters[n] = 0;                     // re-armed for the next step
+  if (want_raw) a.no_speech_prob[n] = expf(row[a.no_speech] - t.mraw) / t.sraw;
+  if (sampling) {
+    const int prev = a.tokens[static_cast<int64_t>(n) * a.ld_tokens + pos];
+    const bool finished = (prev == a.eot);
+    const float logprob = -logf(t.sf);            // logit[arg] - (mf + log sum exp(x - mf)), logit[arg] == mf
+    if (!finished) a.sum_logprobs[n] += logprob;
+    const int next = finished ? a.eot : t.arg;
+    a.tokens[static_cast<int64_t>(n) * a.ld_tokens + pos + 1] = next;
+    if (next != a.eot) atomicAdd(a.n_unfinished, 1);
   }
 }
 
@@ -652,9 +710,11 @@ __global__ void convert_kernel(const TI* __restrict__ src, TO* __restrict__ dst,
     dst[i] = static_cast<TO>(static_cast<float>(src[i]));
 }
 
-// Launch with the programmatic-dependent-launch attribute (see pdl_wait above); OASR_DEC_PDL=0 launches plainly.
+// Launch with the programmatic-dependent-launch attribute (see pdl_wait above) when OASR_DEC_PDL=1; plainly otherwise.
 inline bool pdl_enabled() {
-  static const int v = [] { const char* e = getenv("OASR_DEC_PDL"); return e ? atoi(e) : 1; }();
+  // measured on B200 (profiles/r02_decode_rtf_pdl_ab.txt): inside a CUDA graph the gaps between these kernels are already
+  // ~0 and holding several waiting grids resident costs more than the early weight prefetch gains -> off by default
+  static const int v = [] { const char* e = getenv("OASR_DEC_PDL"); return e ? atoi(e) : 0; }();
   return v != 0;
 }
 template <typename... KArgs, typename... Args>
@@ -779,7 +839,8 @@ extern "C" int oasr_dec_sample(const oasr_dec_sample_args* a, void* stream) {
   OASR_REQUIRE(a != nullptr && a->logits && a->tokens && a->pos_ptr && a->suppress && a->sum_logprobs && a->no_speech_prob &&
                    a->n_unfinished && a->done_flag, "dec_sample: null tensor");
   OASR_REQUIRE(a->n_seq >= 1 && a->n_vocab >= 1, "dec_sample: bad sizes");
-  OASR_CUDA_OK(launch_pdl(dec_sample_kernel, dim3((unsigned)a->n_seq), dim3(256), (cudaStream_t)stream, *a));
+  OASR_REQUIRE(a->scratch && a->counters && a->n_slices >= 1 && a->n_slices <= 64, "dec_sample: scratch / counters / 1 <= n_slices <= 64");
+  OASR_CUDA_OK(launch_pdl(dec_sample_kernel, dim3((unsigned)a->n_slices, (unsigned)a->n_seq), dim3(256), (cudaStream_t)stream, *a));
   OASR_CUDA_OK(launch_pdl(dec_advance_kernel, dim3(1), dim3(1), (cudaStream_t)stream, a->pos_ptr, a->n_unfinished, a->done_flag,
                           (int)a->sample_begin));
   return OASR_OK;

@@ -82,6 +82,9 @@ class DecodeEngine:
         self.n_unfinished = torch.zeros(1, device=dev, dtype=torch.int32)
         self.done = torch.zeros(1, device=dev, dtype=torch.int32)
         self.suppress = torch.zeros(self.V, device=dev, dtype=torch.uint8)
+        self.sample_slices = 16          # blocks per sequence in the sampling kernel
+        self.sample_scratch = z(N, self.sample_slices, 8, dt=torch.float32)
+        self.sample_counters = torch.zeros(N, device=dev, dtype=torch.int32)
         self._w: Optional[dict] = None
         self._w_sig = None
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
@@ -192,6 +195,7 @@ class DecodeEngine:
         s.tokens, s.ld_tokens, s.pos_ptr = ptr(self.tokens), self.tokens.stride(0), ptr(self.pos)
         s.suppress, s.sum_logprobs, s.no_speech_prob = ptr(self.suppress), ptr(self.sum_logprobs), ptr(self.no_speech)
         s.n_unfinished, s.done_flag = ptr(self.n_unfinished), ptr(self.done)
+        s.scratch, s.counters, s.n_slices = ptr(self.sample_scratch), ptr(self.sample_counters), self.sample_slices
         cfg = self._sample_cfg
         s.n_seq, s.n_vocab = n, self.V
         s.sample_begin, s.sot_index, s.suppress_blank, s.blank, s.eot, s.no_speech = cfg
@@ -204,10 +208,11 @@ class DecodeEngine:
         if g is None:
             # one eager run first (kernel modules are loaded lazily on first launch, which must not happen under capture),
             # with the device-side decode state saved and restored around it; the capture itself does not execute
-            state = [t.clone() for t in (self.pos, self.tokens, self.sum_logprobs, self.no_speech, self.n_unfinished, self.done)]
+            live = (self.pos, self.tokens, self.sum_logprobs, self.no_speech, self.n_unfinished, self.done, self.sample_counters)
+            state = [t.clone() for t in live]
             self._enqueue_step(n)
             torch.cuda.synchronize(self.dev)
-            for t, saved in zip((self.pos, self.tokens, self.sum_logprobs, self.no_speech, self.n_unfinished, self.done), state):
+            for t, saved in zip(live, state):
                 t.copy_(saved)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
@@ -249,6 +254,7 @@ class DecodeEngine:
         self.tokens.zero_()
         self.tokens[:n, :P] = tokens.to(device=self.dev, dtype=torch.int32)
         self.pos.zero_(); self.sum_logprobs.zero_(); self.no_speech.zero_(); self.n_unfinished.zero_(); self.done.zero_()
+        self.sample_counters.zero_()
         sup = torch.zeros(self.V, dtype=torch.uint8)
         ids = [t for t in suppress if 0 <= t < self.V]
         if ids:

@@ -203,6 +203,7 @@ def test_sampling_kernel_bookkeeping():
     s.tokens, s.ld_tokens, s.pos_ptr = ptr(eng.tokens), eng.tokens.stride(0), ptr(eng.pos)
     s.suppress, s.sum_logprobs, s.no_speech_prob = ptr(eng.suppress), ptr(eng.sum_logprobs), ptr(eng.no_speech)
     s.n_unfinished, s.done_flag = ptr(eng.n_unfinished), ptr(eng.done)
+    s.scratch, s.counters, s.n_slices = ptr(eng.sample_scratch), ptr(eng.sample_counters), eng.sample_slices
     s.n_seq, s.n_vocab, s.sample_begin, s.sot_index, s.suppress_blank, s.blank, s.eot, s.no_speech = n, V, 2, 0, 1, 220, EOT, 50361
     call("oasr_dec_sample", ctypes.byref(s), stream())
     ref = logits.clone()
@@ -219,6 +220,13 @@ def test_sampling_kernel_bookkeeping():
     eng.logits[:n, EOT] = 30.0
     call("oasr_dec_sample", ctypes.byref(s), stream())
     assert eng.tokens[:n, 3].cpu().tolist() == [EOT] * n and int(eng.done.item()) == 1
+    assert int(eng.sample_counters.abs().sum()) == 0            # the slice counters re-arm themselves
+    # one slice per row gives the same choices as sixteen
+    eng.pos.fill_(1); eng.sum_logprobs.zero_()
+    eng.logits[:n] = logits
+    s.n_slices = 1
+    call("oasr_dec_sample", ctypes.byref(s), stream())
+    assert torch.equal(eng.tokens[:n, 2].cpu(), out) and torch.allclose(eng.sum_logprobs[:3].cpu(), lp[:3].cpu(), rtol=1e-4, atol=1e-4)
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
