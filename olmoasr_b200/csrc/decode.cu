@@ -184,19 +184,31 @@ __global__ void __launch_bounds__(256) dec_linear_direct_kernel(const oasr_dec_l
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
 
-  for (; k0 < K; k0 += 256) {
-    const int kn = k0 + 256;
-    uint4 nb0 = zero, nb1 = zero;
-    if (kn < K) {   // the HBM stream runs one round ahead of the MMAs
-      nb0 = ok0 ? __ldg(reinterpret_cast<const uint4*>(w0 + kn)) : zero;
-      nb1 = ok1 ? __ldg(reinterpret_cast<const uint4*>(w1 + kn)) : zero;
-    }
-    // all x fragments of this round first (2 MT independent L2 / L1 loads in flight), then the MMAs
-    uint4 xa[MT], xb[MT];
+  // x fragments are double-buffered like W: round r + 1's loads (L2 latency each) are in flight under round r's MMAs
+  // (fc2 at K = 3072 is 12 rounds per warp: serialised, the x latency alone was ~8 of its 11.5 us at one sequence)
+  uint4 xa[MT], xb[MT];
+  if (k0 < K) {
 #pragma unroll
     for (int i = 0; i < MT; ++i) {
       xa[i] = load_x8<T>(a, s_stat, i * 16 + g, k0 + 8 * t);
       xb[i] = load_x8<T>(a, s_stat, i * 16 + 8 + g, k0 + 8 * t);
+    }
+  }
+  for (; k0 < K; k0 += 256) {
+    const int kn = k0 + 256;
+    uint4 nb0 = zero, nb1 = zero;
+    uint4 nxa[MT], nxb[MT];
+    if (kn < K) {   // the HBM stream and the x fragments run one round ahead of the MMAs
+      nb0 = ok0 ? __ldg(reinterpret_cast<const uint4*>(w0 + kn)) : zero;
+      nb1 = ok1 ? __ldg(reinterpret_cast<const uint4*>(w1 + kn)) : zero;
+#pragma unroll
+      for (int i = 0; i < MT; ++i) {
+        nxa[i] = load_x8<T>(a, s_stat, i * 16 + g, kn + 8 * t);
+        nxb[i] = load_x8<T>(a, s_stat, i * 16 + 8 + g, kn + 8 * t);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < MT; ++i) { nxa[i] = zero; nxb[i] = zero; }
     }
 #pragma unroll
     for (int i = 0; i < MT; ++i) {
@@ -206,6 +218,8 @@ __global__ void __launch_bounds__(256) dec_linear_direct_kernel(const oasr_dec_l
       DT<T>::mma(acc[i][1], xa[i].z, xb[i].z, xa[i].w, xb[i].w, b1.z, b1.w);
     }
     b0 = nb0; b1 = nb1;
+#pragma unroll
+    for (int i = 0; i < MT; ++i) { xa[i] = nxa[i]; xb[i] = nxb[i]; }
   }
   // fixed-order reduction over the 8 K slices (deterministic), then the epilogue
 #pragma unroll

@@ -71,7 +71,7 @@ class DecodeEngine:
         self.cross_kv = z(L, N * self.n_audio_ctx, 2 * d)
         self.x, self.q, self.h = z(N, d), z(N, d), z(N, 4 * d)
         self.scores = z(N, self.H, 1536, dt=torch.float32)
-        self.max_splits = 16
+        self.max_splits = 8       # key-range splits of the cross-attention at small batches (each split's fp32 partial is re-read by the out projection)
         self.part_self = z(1, N, d, dt=torch.float32)
         self.part_cross = z(self.max_splits, N, d, dt=torch.float32)
         self.logits = z(N, self.V, dt=torch.float32)
@@ -162,7 +162,7 @@ class DecodeEngine:
             _lib.LAUNCH_COUNT -= 1      # an unsplit key range runs as ONE fused kernel (scores + softmax + P V), not two
 
     def cross_splits(self, n: int) -> int:
-        """Key-range splits of the cross-attention so that n x H x splits CTAs cover the 148 SMs twice (>= 94 keys each)."""
+        """Key-range splits of the cross-attention so that n x H x splits CTAs cover the 148 SMs about twice (>= 188 keys each)."""
         return max(1, min(self.max_splits, math.ceil(2 * 148 / (n * self.H))))
 
     def _enqueue_step(self, n: int):
