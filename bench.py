@@ -261,7 +261,8 @@ def our_arm(args):
     slabs = model.use_slabs(direct_grads=(ddp_impl == "slab"))
     if world > 1 and ddp_impl == "slab":
         from olmoasr_b200.ddp import SlabGradSync
-        sync = SlabGradSync(model, slabs, bucket_bytes=int(os.environ.get("OASR_BUCKET_MB", "256")) << 20)
+        sync = SlabGradSync(model, slabs, bucket_bytes=int(os.environ.get("OASR_BUCKET_MB", "256")) << 20,
+                            tail_bucket_bytes=int(os.environ.get("OASR_TAIL_BUCKET_MB", "32")) << 20)
     elif world > 1:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], output_device=local_rank)
         slabs.invalidate()      # DDP's constructor broadcast rank 0's weights into the masters behind autograd's back

@@ -359,7 +359,7 @@ def _slab_sync_worker(rank, world, port, out):
     net = _ToySlabModel()
     layout = [p for ps, _ in net.grad_units() for p in ps]
     slabs = ParamSlabs(net, layout, shadows=False)
-    sync = SlabGradSync(net, slabs, bucket_bytes=1)      # every unit its own segment
+    sync = SlabGradSync(net, slabs, bucket_bytes=1, tail_bucket_bytes=1)      # every unit its own segment
     assert len(sync.segments) == 3 and sync.segments[0][0] == 0 and sync.segments[-1][1] == slabs.numel
     assert all(a[1] == b[0] for a, b in zip(sync.segments, sync.segments[1:]))
     launched_early = []

@@ -32,7 +32,8 @@ def main():
     net, sync = model, None
     if impl == "slab":
         from olmoasr_b200.ddp import SlabGradSync
-        sync = SlabGradSync(model, slabs, bucket_bytes=int(os.environ.get("OASR_BUCKET_MB", "256")) << 20)
+        sync = SlabGradSync(model, slabs, bucket_bytes=int(os.environ.get("OASR_BUCKET_MB", "256")) << 20,
+                            tail_bucket_bytes=int(os.environ.get("OASR_TAIL_BUCKET_MB", "32")) << 20)
     else:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local])
     opt = FusedAdamW(model.parameters(), slabs=slabs)
