@@ -153,7 +153,7 @@ def test_width_goldens_pin_the_oracle_at_benchmark_widths(name, golden_dir):
     logits = OM.model_forward(p, dims, mel, ti, pm, train_model=True)
     loss = OM.token_ce(logits, ty)
     assert torch.allclose(logits.detach()[:, ::16, ::997], g["logits_fp32_sample"], atol=2e-4, rtol=1e-4)
-    assert float(loss) == pytest.approx(g["loss_fp32"], rel=1e-5)
+    assert float(loss.detach()) == pytest.approx(g["loss_fp32"], rel=1e-5)
     loss.backward()
     for k, n in g["grad_norms"].items():
         assert float(p[k].grad.double().norm()) == pytest.approx(n, rel=2e-3, abs=1e-7), k
