@@ -52,6 +52,8 @@ __global__ void unpermute_conv_wgrad_kernel(const float* __restrict__ src, float
 // exactly that structure; any other additive mask raises err[0] (reported by the host as a ValueError).
 __global__ void __launch_bounds__(256)
 mask_to_kvlen_kernel(const float* __restrict__ mask, int32_t* __restrict__ kv_len, int32_t* __restrict__ err, int S) {
+  // grid (batch, slices): every block recounts the zeros of row 0 (S floats), then verifies its slice of rows with
+  // 16-byte loads (the first version used one block per sample: 0.44 ms for the 25.7 MB mask of a 32-clip batch)
   const float* m = mask + static_cast<int64_t>(blockIdx.x) * S * S;
   __shared__ int s_len;
   __shared__ int s_bad;
@@ -63,17 +65,29 @@ mask_to_kvlen_kernel(const float* __restrict__ mask, int32_t* __restrict__ kv_le
   if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_len, cnt);
   __syncthreads();
   const int len = s_len;
+  const int rows_per = (S + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per, r1 = min(S, r0 + rows_per);
   int bad = 0;
-  const int64_t n = static_cast<int64_t>(S) * S;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-    const int c = static_cast<int>(i % S);
-    const float v = m[i];
-    bad |= (c < len) ? (v != 0.f) : !(v < -1e30f);
+  if ((S & 3) == 0 && (reinterpret_cast<uintptr_t>(m) & 15) == 0) {
+    const int vec = S >> 2;
+    for (int64_t i = static_cast<int64_t>(r0) * vec + threadIdx.x; i < static_cast<int64_t>(r1) * vec; i += blockDim.x) {
+      const int c = static_cast<int>(i % vec) * 4;
+      const float4 v = *reinterpret_cast<const float4*>(m + i * 4);
+      const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bad |= (c + j < len) ? (x[j] != 0.f) : !(x[j] < -1e30f);
+    }
+  } else {
+    for (int64_t i = static_cast<int64_t>(r0) * S + threadIdx.x; i < static_cast<int64_t>(r1) * S; i += blockDim.x) {
+      const int c = static_cast<int>(i % S);
+      const float v = m[i];
+      bad |= (c < len) ? (v != 0.f) : !(v < -1e30f);
+    }
   }
   if (bad) s_bad = 1;
   __syncthreads();
   if (threadIdx.x == 0) {
-    kv_len[blockIdx.x] = len;
+    if (blockIdx.y == 0) kv_len[blockIdx.x] = len;
     if (s_bad) atomicOr(err, 1);
   }
 }
@@ -291,7 +305,7 @@ extern "C" int oasr_unpermute_conv_wgrad(const float* src, float* dst, int64_t c
 
 extern "C" int oasr_mask_to_kvlen(const float* mask, int32_t* kv_len, int32_t* err, int64_t batch, int64_t S, void* stream) {
   OASR_REQUIRE(batch > 0 && S > 0 && mask && kv_len && err, "mask_to_kvlen: bad arguments");
-  mask_to_kvlen_kernel<<<(unsigned)batch, 256, 0, (cudaStream_t)stream>>>(mask, kv_len, err, (int)S);
+  mask_to_kvlen_kernel<<<dim3((unsigned)batch, 16), 256, 0, (cudaStream_t)stream>>>(mask, kv_len, err, (int)S);
   OASR_LAUNCH_CHECK();
   return OASR_OK;
 }
