@@ -14,7 +14,9 @@
 // into an fp32 scratch buffer (converted to bf16 afterwards).  (Per-thread red.global.add.v4 made the whole kernel
 // atomics-bound: ~6500 cycles per tile pair against ~1300 of tensor work.)
 // 8 compute warps (two per TMEM lane quarter, each taking half of the 128 key columns; packed FFMA2 / FADD2 /
-// FMUL2 math) + TMA warp + MMA warp; S / dP are released to the MMA warp as soon as they sit in registers.
+// FMUL2 math) + TMA warp + MMA warp + 4 dQ-drain warps; S / dP are released to the MMA warp as soon as they sit in
+// registers.  The dQ drain (TMEM -> fp32 smem tile -> TMA reduce-add) has its own warpgroup: on the compute warps it
+// cost 1300 of 3850 cycles per query tile (profiles/r02_attention_bwd_trace_before.txt).
 // TMEM map (512 cols): S 0..127 | dP 128..255 | dV 256..319 | dK 320..383 | dQ 384..447.
 #include "common.cuh"
 #include "ptx_sm100.cuh"
@@ -37,7 +39,13 @@ constexpr int BWD_TILES = 2 * TILE_BYTES + Q_STAGES * 2 * TILE_BYTES + 2 * P_BYT
 constexpr int BWD_SMEM = BWD_TILES + 256;
 constexpr int TMEM_COLS = 512;
 constexpr int S_COL = 0, DP_COL = 128, DV_COL = 256, DK_COL = 320, DQ_COL = 384;
-constexpr int COMPUTE_REGS = 184, CONTROL_REGS = 136;   // 8 * 184 + 4 * 136 == 12 * 168
+#ifndef OASR_BWD_DRAIN_WG
+#define OASR_BWD_DRAIN_WG 1
+#endif
+constexpr bool DRAIN_WG = OASR_BWD_DRAIN_WG != 0;
+constexpr int BWD_THREADS = DRAIN_WG ? 512 : 384;
+// register pool: 8 * 184 + 4 * 96 + 4 * 48 == 16 * 128 (drain warpgroup)   |   8 * 184 + 4 * 136 == 12 * 168
+constexpr int COMPUTE_REGS = 184, CONTROL_REGS = DRAIN_WG ? 96 : 136, DRAIN_REGS = 48;
 
 struct BwdParams {
   const float* lse;   // (B,H,Tq) log2 domain
@@ -51,6 +59,29 @@ struct BwdParams {
   int causal;
   float scale, scale_log2;
 };
+
+#ifdef OASR_ATTN_TRACE
+// Debug build only (python -m olmoasr_b200.build --variant attn_trace -DOASR_ATTN_TRACE): one CTA in the middle of the
+// grid stamps clock64() at every phase boundary; tools/trace_attention.py prints the per-phase cycle table.
+__device__ unsigned long long g_bwd_trace[4][512];
+#define TRACE_DECL(role_)                                                                                     \
+  const bool tr_on = (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) == (gridDim.x * gridDim.y * gridDim.z) / 2 + gridDim.x / 2 && \
+                     lane == 0;                                                                               \
+  const int tr_role = (role_);                                                                                \
+  int tr_n = 0;
+#define TR(id_)                                                                                               \
+  do {                                                                                                        \
+    if (tr_on && tr_n < 511) g_bwd_trace[tr_role][++tr_n] = (static_cast<unsigned long long>(id_) << 48) | (clock64() & 0xffffffffffffull); \
+  } while (0)
+#define TRACE_END()                                                                                           \
+  do {                                                                                                        \
+    if (tr_on) g_bwd_trace[tr_role][0] = tr_n;                                                                \
+  } while (0)
+#else
+#define TRACE_DECL(role_)
+#define TR(id_)
+#define TRACE_END()
+#endif
 
 __device__ __forceinline__ void store_swizzled_row32(uint32_t tile_base, int r, int cc, const float (&x)[32]) {
   // 32 consecutive bf16 columns [cc*32, cc*32+32) of row r into a two-half [128][128B] swizzled tile
@@ -66,11 +97,12 @@ __device__ __forceinline__ void store_swizzled_row32(uint32_t tile_base, int r, 
   }
 }
 
-// 384 threads: warps 0..7 compute (warp w: TMEM lane quarter w%4, key-column half w/4), warp 8 TMA producer,
-// warp 9 MMA issuer + TMEM owner, warps 10-11 idle.  setmaxnreg gives the compute warps 224 registers so that a
-// thread holds its 64 S and 64 dP values at once: both TMEM buffers are released right after the load (bar_free) and
-// the MMA warp issues S / dP of the NEXT query tile underneath this tile's exp / dS math.
-__global__ void __launch_bounds__(384, 1)
+// 512 threads: warps 0..7 compute (warp w: TMEM lane quarter w%4, key-column half w/4), warp 8 TMA producer,
+// warp 9 MMA issuer + TMEM owner, warps 10-11 idle, warps 12..15 dQ drain (lane quarter w%4).  setmaxnreg gives the
+// compute warps 184 registers so that a thread holds its 64 S and 64 dP values at once: both TMEM buffers are released
+// right after the load (bar_free) and the MMA warp issues S / dP of the NEXT query tile underneath this tile's exp / dS
+// math.
+__global__ void __launch_bounds__(BWD_THREADS, 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                      const __grid_constant__ CUtensorMap tmDQ, const BwdParams p) {
@@ -84,7 +116,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t& bar_done = bars[5];
   uint64_t* bar_q_full = bars + 6;
   uint64_t* bar_q_empty = bars + 6 + Q_STAGES;
-  uint32_t& tmem_slot = *reinterpret_cast<uint32_t*>(bars + 6 + 2 * Q_STAGES);
+  uint64_t& bar_dqfree = bars[6 + 2 * Q_STAGES];   // dQ of the previous tile read out of TMEM (4 drain-warp arrivals)
+  uint32_t& tmem_slot = *reinterpret_cast<uint32_t*>(bars + 7 + 2 * Q_STAGES);
 
   const uint32_t sbase = ptx::smem_u32(smem_raw);
   if ((sbase & 1023u) != 0) {
@@ -114,11 +147,17 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     ptx::mbar_init(ptx::smem_u32(&bar_pds), 8);
     ptx::mbar_init(ptx::smem_u32(&bar_dq), 1);
     ptx::mbar_init(ptx::smem_u32(&bar_done), 1);
+    ptx::mbar_init(ptx::smem_u32(&bar_dqfree), 4);
     for (int s = 0; s < Q_STAGES; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bar_q_full[s]), 1);
       ptx::mbar_init(ptx::smem_u32(&bar_q_empty[s]), 1);
     }
     ptx::fence_barrier_init();
+    if (n_iter > 0) {   // K / V are on their way while the CTA is still setting up (TMEM allocation, __syncthreads)
+      ptx::mbar_arrive_expect_tx(ptx::smem_u32(&bar_kv), 2 * TILE_BYTES);
+      ptx::tma_load_2d(sK, &tmK, ptx::smem_u32(&bar_kv), h * HD, b * p.Tkv + kv0);
+      ptx::tma_load_2d(sV, &tmV, ptx::smem_u32(&bar_kv), h * HD, b * p.Tkv + kv0);
+    }
   }
   if (warp == 9) {
     ptx::tmem_alloc<TMEM_COLS>(ptx::smem_u32(&tmem_slot));
@@ -129,17 +168,67 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   ptx::tc_fence_after();
   const uint32_t tmem = tmem_slot;
 
-  if (warp >= 8) {
+  if (DRAIN_WG && warp >= 12) {
+    ptx::setmaxnreg_dec<DRAIN_REGS>();
+    // ------------------------------ dQ drain warpgroup ------------------------------
+    // dQ of query tile `it`: TMEM (this warp's 32 lanes x 64 columns) -> swizzled fp32 smem rows (two 32-column halves of
+    // [128][128 B]) -> one TMA reduce-add per half into the fp32 scratch.  Rows past Tq carry exact zeros (their P and dS
+    // rows are zero), rows past the tensor are clipped by TMA.
+    TRACE_DECL(3)
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t t_lane = static_cast<uint32_t>(quarter * 32) << 16;
+    const bool issuer = (warp == 12 && lane == 0);
+    for (int it = 0; it < n_iter; ++it) {
+      ptx::mbar_wait(ptx::smem_u32(&bar_dq), it & 1);
+      TR(20);
+      ptx::tc_fence_after();
+      if (issuer) ptx::tma_store_wait_read<0>();   // the previous reduce has finished reading the staging tile
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        ptx::tc_ld_32x32b_x32(tmem + t_lane + DQ_COL + half * 32, v);
+        ptx::tc_wait_ld();
+        if (half == 1) {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_dqfree));   // dQ TMEM may be overwritten
+        } else {
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const uint32_t addr = sDQ + half * (DQ_BYTES / 2) + r * 128 + ((q4 ^ (r & 7)) << 4);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(__uint_as_float(v[4 * q4]) * p.scale),
+                       "f"(__uint_as_float(v[4 * q4 + 1]) * p.scale), "f"(__uint_as_float(v[4 * q4 + 2]) * p.scale),
+                       "f"(__uint_as_float(v[4 * q4 + 3]) * p.scale)
+                       : "memory");
+        }
+      }
+      TR(21);
+      ptx::fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (issuer) {
+        const int qrow = b * p.Tq + (i_begin + it) * BQ;
+        ptx::tma_reduce_add_2d(&tmDQ, sDQ, h * HD, qrow);
+        ptx::tma_reduce_add_2d(&tmDQ, sDQ + DQ_BYTES / 2, h * HD + 32, qrow);
+        ptx::tma_store_commit();
+      }
+      TR(22);
+    }
+    if (issuer) ptx::tma_store_wait_read<0>();
+    TRACE_END();
+  } else if (warp >= 8) {
     ptx::setmaxnreg_dec<CONTROL_REGS>();
     if (warp == 8 && lane == 0 && n_iter > 0) {
       // ------------------------------ TMA producer ------------------------------
-      ptx::mbar_arrive_expect_tx(ptx::smem_u32(&bar_kv), 2 * TILE_BYTES);
-      ptx::tma_load_2d(sK, &tmK, ptx::smem_u32(&bar_kv), h * HD, b * p.Tkv + kv0);
-      ptx::tma_load_2d(sV, &tmV, ptx::smem_u32(&bar_kv), h * HD, b * p.Tkv + kv0);
+      TRACE_DECL(2)
+      TR(1);
       int s = 0;
       uint32_t ph = 0;
       for (int it = 0; it < n_iter; ++it) {
         ptx::mbar_wait(ptx::smem_u32(&bar_q_empty[s]), ph ^ 1);
+        TR(2);
         const uint32_t full = ptx::smem_u32(&bar_q_full[s]);
         ptx::mbar_arrive_expect_tx(full, 2 * TILE_BYTES);
         const int qrow = b * p.Tq + (i_begin + it) * BQ;
@@ -147,8 +236,11 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         ptx::tma_load_2d(sQ0 + s * 2 * TILE_BYTES + TILE_BYTES, &tmdO, full, h * HD, qrow);
         if (++s == Q_STAGES) { s = 0; ph ^= 1; }
       }
+      TRACE_END();
     } else if (warp == 9 && n_iter > 0) {
       // ------------------------------ MMA issuer (whole warp convergent; elect.sync picks the issuing lane) ------------------------------
+      TRACE_DECL(1)
+      TR(1);
       constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, 128, 0, 0);    // S, dP
       constexpr uint32_t idesc_kv = ptx::umma_idesc_bf16(128, 64, 1, 1);    // dV, dK
       constexpr uint32_t idesc_dq = ptx::umma_idesc_bf16(128, 64, 0, 1);    // dQ
@@ -181,9 +273,12 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         __syncwarp();
       };
       ptx::mbar_wait(ptx::smem_u32(&bar_kv), 0);
+      TR(2);
       ptx::mbar_wait(ptx::smem_u32(&bar_q_full[0]), 0);
+      TR(3);
       ptx::tc_fence_after();
       issue_s_dp(0);
+      TR(4);
       int st = 0;
       uint32_t st_ph = 0;
       for (int it = 0; it < n_iter; ++it) {
@@ -192,32 +287,45 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         if (st_n == Q_STAGES) { st_n = 0; ph_n ^= 1; }
         if (it + 1 < n_iter) {   // next tile's S / dP as soon as this tile's have been read into registers
           ptx::mbar_wait(ptx::smem_u32(&bar_q_full[st_n]), ph_n);
+          TR(5);
           ptx::mbar_wait(ptx::smem_u32(&bar_free), it & 1);
+          TR(6);
           ptx::tc_fence_after();
           issue_s_dp(st_n);
+          TR(7);
         }
         const uint32_t dob = doB_lo0 + st * STAGE_LO, qb = qB_lo0 + st * STAGE_LO;
-        ptx::mbar_wait(ptx::smem_u32(&bar_pds), it & 1);  // P, dS in smem; dQ TMEM drained
+        ptx::mbar_wait(ptx::smem_u32(&bar_pds), it & 1);  // P, dS in smem (without the drain warpgroup: and dQ TMEM drained)
+        TR(8);
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < BQ / 16; ++k) {  // reduction over the 128 query rows, 16 at a time
-          ptx::tc_mma_f16_lh(tmem + DV_COL, pT_lo + k * (2048 >> 4), hi_mnA, dob + k * (2048 >> 4), hi_mnB, idesc_kv,
-                             (it > 0 || k > 0) ? 1u : 0u);
-          ptx::tc_mma_f16_lh(tmem + DK_COL, dsT_lo + k * (2048 >> 4), hi_mnA, qb + k * (2048 >> 4), hi_mnB, idesc_kv,
-                             (it > 0 || k > 0) ? 1u : 0u);
-        }
-#pragma unroll
-        for (int k = 0; k < BKV / 16; ++k)   // dQ_i = dS K : reduction over the 128 keys
-          ptx::tc_mma_f16_lh(tmem + DQ_COL, dsK_lo + (k >> 2) * ((P_BYTES / 2) >> 4) + (k & 3) * 2, hi_k,
-                             kB_lo + k * (2048 >> 4), hi_mnB, idesc_dq, k > 0);
-        ptx::tc_commit(ptx::smem_u32(&bar_dq));
-        ptx::tc_commit(ptx::smem_u32(&bar_q_empty[st]));
-        if (it + 1 == n_iter) ptx::tc_commit(ptx::smem_u32(&bar_done));
+          for (int k = 0; k < BQ / 16; ++k) {  // reduction over the 128 query rows, 16 at a time
+            ptx::tc_mma_f16_lh(tmem + DV_COL, pT_lo + k * (2048 >> 4), hi_mnA, dob + k * (2048 >> 4), hi_mnB, idesc_kv,
+                               (it > 0 || k > 0) ? 1u : 0u);
+            ptx::tc_mma_f16_lh(tmem + DK_COL, dsT_lo + k * (2048 >> 4), hi_mnA, qb + k * (2048 >> 4), hi_mnB, idesc_kv,
+                               (it > 0 || k > 0) ? 1u : 0u);
+          }
         }
         __syncwarp();
+        if (DRAIN_WG && it > 0) {   // the drain warps have read dQ of the previous tile out of TMEM
+          ptx::mbar_wait(ptx::smem_u32(&bar_dqfree), (it - 1) & 1);
+          ptx::tc_fence_after();
+        }
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < BKV / 16; ++k)   // dQ_i = dS K : reduction over the 128 keys
+            ptx::tc_mma_f16_lh(tmem + DQ_COL, dsK_lo + (k >> 2) * ((P_BYTES / 2) >> 4) + (k & 3) * 2, hi_k,
+                               kB_lo + k * (2048 >> 4), hi_mnB, idesc_dq, k > 0);
+          ptx::tc_commit(ptx::smem_u32(&bar_dq));
+          ptx::tc_commit(ptx::smem_u32(&bar_q_empty[st]));
+          if (it + 1 == n_iter) ptx::tc_commit(ptx::smem_u32(&bar_done));
+        }
+        __syncwarp();
+        TR(9);
         st = st_n; st_ph = ph_n;
       }
+      TRACE_END();
     }
   } else {
     // ----------------------------- compute warps -----------------------------
@@ -227,6 +335,14 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int r = quarter * 32 + lane;
     const uint32_t t_lane = static_cast<uint32_t>(quarter * 32) << 16;
     const float c = p.scale_log2;
+    TRACE_DECL(0)
+#ifdef OASR_ATTN_TRACE
+    const bool tr_keep = tr_on && warp == 0;
+#define TRC(id_) do { if (tr_keep) TR(id_); } while (0)
+#else
+#define TRC(id_)
+#endif
+    TRC(1);
 
     // dQ of query tile `it`: this warp's 32 of the 64 columns -> swizzled fp32 smem rows -> one TMA reduce-add per
     // column half (128 threads = the 4 warps sharing `chalf` cooperate through named barrier 1 + chalf)
@@ -234,13 +350,16 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const bool issuer = (quarter == 0 && lane == 0);
     auto drain_dq = [&](int it) {
       ptx::mbar_wait(ptx::smem_u32(&bar_dq), it & 1);
+      TRC(20);
       ptx::tc_fence_after();
       uint32_t v[32];
       ptx::tc_ld_32x32b_x32(tmem + t_lane + DQ_COL + chalf * 32, v);
       ptx::tc_wait_ld();
       ptx::tc_fence_before();
+      TRC(21);
       if (issuer) ptx::tma_store_wait_read<0>();               // previous reduce has finished reading the staging tile
       asm volatile("bar.sync %0, 128;" ::"r"(1 + chalf) : "memory");
+      TRC(22);
 #pragma unroll
       for (int q4 = 0; q4 < 8; ++q4) {
         const uint32_t addr = sDQh + r * 128 + ((q4 ^ (r & 7)) << 4);
@@ -251,6 +370,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
       ptx::fence_proxy_async_smem();
       asm volatile("bar.sync %0, 128;" ::"r"(1 + chalf) : "memory");
+      TRC(23);
       if (issuer) {
         // rows past Tq carry exact zeros (their P and dS rows are zero), rows past the tensor are clipped by TMA
         ptx::tma_reduce_add_2d(&tmDQ, sDQh, h * HD + chalf * 32, b * p.Tq + (i_begin + it) * BQ);
@@ -278,7 +398,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       int limit = kv_valid - kv0;                     // visible keys of this tile: [0, limit)
       if (p.causal) limit = min(limit, qi - kv0 + 1);
       if (!q_ok) limit = 0;
+      TRC(10);
       ptx::mbar_wait(ptx::smem_u32(&bar_sdp), it & 1);
+      TRC(11);
       ptx::tc_fence_after();
       uint32_t sv[64], dv[64];
       ptx::tc_ld_32x32b_x32(tmem + t_lane + S_COL + chalf * 64, reinterpret_cast<uint32_t (&)[32]>(sv[0]));
@@ -289,6 +411,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_free));   // S / dP TMEM may be overwritten
+      TRC(12);
       // All the exp / dS math happens BEFORE waiting for the previous tile's dV/dK/dQ MMAs (which still read sP / sdS):
       // the results wait in registers as packed bf16, so the compute warps never idle behind the tensor pipe.
       const float2 c2 = make_float2(c, c), nl2 = make_float2(-lse, -lse), nd2 = make_float2(-dlt, -dlt);
@@ -316,7 +439,12 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
       };
       if (__all_sync(0xffffffffu, limit >= (chalf + 1) * 64)) p_ds(std::false_type{}); else p_ds(std::true_type{});
-      if (it > 0) drain_dq(it - 1);   // dV/dK/dQ MMAs of the previous tile retired => sP / sdS reusable
+      TRC(13);
+      if (it > 0) {   // dV/dK/dQ MMAs of the previous tile retired => sP / sdS reusable
+        if (DRAIN_WG) ptx::mbar_wait(ptx::smem_u32(&bar_dq), (it - 1) & 1);
+        else drain_dq(it - 1);
+      }
+      TRC(14);
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         const int cc = chalf * 2 + hh;
@@ -334,11 +462,13 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_pds));
+      TRC(15);
     }
-    if (n_iter > 0) {
+    if (!DRAIN_WG && n_iter > 0) {
       drain_dq(n_iter - 1);
       if (issuer) ptx::tma_store_wait_read<0>();
     }
+    TRC(30);
 
     // ---- dK / dV for key row r of this tile (this warp's 32 of the 64 columns)
     const int ki = kv0 + r;
@@ -346,6 +476,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       ptx::mbar_wait(ptx::smem_u32(&bar_done), 0);
       ptx::tc_fence_after();
     }
+    TRC(31);
     bf16* dk_row = p.dk + (static_cast<int64_t>(b) * p.Tkv + ki) * p.lddk + h * HD;
     bf16* dv_row = p.dv + (static_cast<int64_t>(b) * p.Tkv + ki) * p.lddv + h * HD;
     {
@@ -376,6 +507,10 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
       }
     }
+    TRC(32);
+#ifdef OASR_ATTN_TRACE
+    if (tr_keep) TRACE_END();
+#endif
   }
 
   ptx::tc_fence_before();
@@ -437,6 +572,12 @@ __global__ void f32_rows_to_bf16_kernel(const float* __restrict__ src, bf16* __r
 
 using namespace oasr;
 
+#ifdef OASR_ATTN_TRACE
+extern "C" OASR_API int oasr_debug_bwd_trace(unsigned long long* host_out) {   // 4 x 512 words
+  return cudaMemcpyFromSymbol(host_out, g_bwd_trace, sizeof(unsigned long long) * 4 * 512) == cudaSuccess ? 0 : 1;
+}
+#endif
+
 extern "C" int oasr_attention_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                                   const void* o, int64_t ldo, const void* dout, int64_t lddo, const float* lse,
                                   float* delta, float* dq_accum, void* dq, int64_t lddq, void* dk, int64_t lddk,
@@ -471,7 +612,7 @@ extern "C" int oasr_attention_bwd(const void* q, int64_t ldq, const void* k, int
     attr_set = true;
   }
   dim3 grid((unsigned)ceil_div(Tkv, BKV), (unsigned)H, (unsigned)B);
-  attention_bwd_kernel<<<grid, 384, BWD_SMEM, st>>>(tmQ, tmK, tmV, tmdO, tmDQ, p);
+  attention_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, st>>>(tmQ, tmK, tmV, tmdO, tmDQ, p);
   OASR_LAUNCH_CHECK();
   const int64_t rows = B * Tq;
   int64_t blocks = ceil_div(rows * (H * HD / 8), 256);

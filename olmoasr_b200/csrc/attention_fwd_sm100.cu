@@ -16,7 +16,7 @@
 // The softmax warpgroups therefore run back to back (MUFU-bound) and the tensor pipe works underneath them.
 //
 // Thread r of a warpgroup owns score row r (= TMEM lane r): the row maximum and sum need no shuffles.
-// TMEM (512 cols): S0 0..127 | S1 128..255 | O0 256..319 | O1 320..383.  O is accumulated by the P*V MMAs
+// TMEM (512 cols): S0 0..127 | S1 128..255 | O0 256..319 | O1 320..383 | P0 384..447 | P1 448..511.  O is accumulated by the P*V MMAs
 // directly in TMEM; it is rescaled (tcgen05.ld -> scale -> tcgen05.st) only when a row maximum grows by more
 // than 2^8 -- otherwise the stale maximum is kept (probabilities stay <= 256; exact after the final 1/l).
 // Scale/subtract and the row sum use packed FFMA2 / FADD2, the maximum FMNMX3.  P goes to smem as bf16 in the
@@ -35,10 +35,20 @@ constexpr int BKV = 128;
 constexpr int KV_STAGES = 3;
 constexpr int TILE_BYTES = 128 * HD * 2;     // 16 KB: a [128 rows][64 bf16] swizzled tile
 constexpr int P_BYTES = BQ * BKV * 2;        // 32 KB: two 64-key halves of [128][128B]
-constexpr int ATT_TILES = 2 * TILE_BYTES /*Q0,Q1*/ + KV_STAGES * 2 * TILE_BYTES /*K,V*/ + 2 * P_BYTES;  // 192 KB
+// P (bf16) as the A operand of the P V MMA: 1 = written back to TMEM (tcgen05.st, consumed by a TMEM-A MMA), 0 = through
+// swizzled shared memory.  Through smem a key tile moves 256 KB over the 128 B/clk shared-memory port (Q K^T operands
+// 64, P stores 64, P V operands 96, K/V TMA writes 32); in TMEM the P stores and the P operand reads (128 KB) disappear.
+// Measured (profiles/r02_attention_fwd_ptmem_ab.txt): parity green, but 0.528 ms vs 0.485 ms for the encoder shape -- the
+// forward is paced by the softmax warps (MUFU), not by the shared-memory port, and tcgen05.st + wait::st is a longer
+// tail than 16 STS.128.  Kept as an A/B switch, default off.
+#ifndef OASR_FWD_P_TMEM
+#define OASR_FWD_P_TMEM 0
+#endif
+constexpr bool P_TMEM = OASR_FWD_P_TMEM != 0;
+constexpr int ATT_TILES = 2 * TILE_BYTES /*Q0,Q1*/ + KV_STAGES * 2 * TILE_BYTES /*K,V*/ + (P_TMEM ? 0 : 2 * P_BYTES);  // 128 / 192 KB
 constexpr int ATT_SMEM = ATT_TILES + 256;
 constexpr int TMEM_COLS = 512;
-constexpr int S_COL = 0, O_COL = 256;        // + t*128 / + t*64
+constexpr int S_COL = 0, O_COL = 256, P_COL = 384;   // + t*128 / + t*64 / + t*64 (128 bf16 keys = 64 columns)
 constexpr float RESCALE_LOG2 = 8.0f;
 constexpr int SOFTMAX_REGS = 224, CONTROL_REGS = 56;   // 8 * SOFTMAX + 4 * CONTROL == 12 * 168
 // Share of the exponentials of an unmasked tile evaluated on the FMA pipe (exp2_poly2) instead of MUFU.EX2:
@@ -162,9 +172,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const uint32_t vlo = v_lo0 + stage * STAGE_LO;
         if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BKV / 16; ++k)
-            ptx::tc_mma_f16_lh(tmem + O_COL + t * HD, p_lo[t] + (k >> 2) * ((P_BYTES / 2) >> 4) + (k & 3) * 2, hi_k,
-                               vlo + k * (2048 >> 4), hi_v, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BKV / 16; ++k) {
+            if (P_TMEM)   // 16 keys = 8 TMEM columns of packed bf16 pairs
+              ptx::tc_mma_f16_ts_lh(tmem + O_COL + t * HD, tmem + P_COL + t * (BKV / 2) + k * 8, vlo + k * (2048 >> 4), hi_v,
+                                    idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+            else
+              ptx::tc_mma_f16_lh(tmem + O_COL + t * HD, p_lo[t] + (k >> 2) * ((P_BYTES / 2) >> 4) + (k & 3) * 2, hi_k,
+                                 vlo + k * (2048 >> 4), hi_v, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+          }
           ptx::tc_commit(ptx::smem_u32(&bar_pv[t]));
         }
         __syncwarp();
@@ -218,6 +233,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const uint32_t t_s = tmem + t_lane + S_COL + t * BKV;
     const uint32_t t_o = tmem + t_lane + O_COL + t * HD;
     const uint32_t sPt = sP + t * P_BYTES;
+    const uint32_t t_p = tmem + t_lane + P_COL + t * (BKV / 2);
     const float c = p.scale_log2;
     const int n_t = n_kv[t];
     float m = -INFINITY, l = 0.f;
@@ -284,6 +300,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       // side).  Masked tiles keep MUFU for every element so that -inf maps to exactly 0.
       auto emit_p = [&](auto poly_tag) {
         constexpr int POLY = decltype(poly_tag)::value;
+        uint32_t pk[32];   // P_TMEM: 64 keys of this row as packed bf16 pairs
 #pragma unroll
         for (int cc = 0; cc < BKV / 32; ++cc) {
           const uint32_t half_base = sPt + (cc >> 1) * (P_BYTES / 2) + r * 128;
@@ -300,19 +317,27 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
               sums[e] = __fadd2_rn(sums[e], pe);
               w[e] = pack_bf16x2(pe.x, pe.y);
             }
-            const int chunk = (cc & 1) * 4 + q4;       // 16-byte chunk index within the 128-byte row
-            const uint32_t addr = half_base + ((chunk ^ (r & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
-                         : "memory");
+            if (P_TMEM) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) pk[(cc & 1) * 16 + q4 * 4 + e] = w[e];
+            } else {
+              const int chunk = (cc & 1) * 4 + q4;       // 16-byte chunk index within the 128-byte row
+              const uint32_t addr = half_base + ((chunk ^ (r & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                           : "memory");
+            }
           }
+          if (P_TMEM && (cc & 1)) ptx::tc_st_32x32b_x32(t_p + (cc >> 1) * 32, pk);
         }
+        if (P_TMEM) ptx::tc_wait_st();
       };
       // ncu of the MUFU-only build (profiles/r01_ncu_kernel_metrics.txt): XU pipe 59.5 %, issue slots 36.7 %, tensor
       // pipe 29.7 % -- 128 x 128 ex2 per tile at 16 / clk / SM is twice the tile's MMA time, so a share of the
       // exponentials moves to the FMA pipe (OASR_ATTN_POLY; measured per build in profiles/r02_attention_poly_ab.txt)
-      if (OASR_ATTN_POLY != 0 && limit >= BKV) emit_p(std::integral_constant<int, OASR_ATTN_POLY>{});
+      // (warp-uniform choice: with P_TMEM both paths contain .sync.aligned tcgen05.st)
+      if (OASR_ATTN_POLY != 0 && __all_sync(0xffffffffu, limit >= BKV)) emit_p(std::integral_constant<int, OASR_ATTN_POLY>{});
       else emit_p(std::integral_constant<int, 0>{});
-      ptx::fence_proxy_async_smem();
+      if (!P_TMEM) ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_p[t]));

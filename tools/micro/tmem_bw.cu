@@ -25,7 +25,7 @@ __device__ __forceinline__ void ld_16x128b_x16(uint32_t a, uint32_t (&r)[32]) {
     : "r"(a) : "memory");
 }
 
-template <int SHAPE>
+template <int SHAPE, int PIPE>
 __global__ void k(unsigned long long* out, uint32_t* sink, int iters) {
   __shared__ uint32_t slot;
   const int warp = threadIdx.x >> 5;
@@ -41,6 +41,15 @@ __global__ void k(unsigned long long* out, uint32_t* sink, int iters) {
   __syncthreads();
   const long long t0 = clock64();
   for (int it = 0; it < iters; ++it) {
+    if (PIPE) {   // four loads in flight (128 registers), one wait: what the attention kernels do per tile
+      uint32_t r0[32], r1[32], r2[32], r3[32];
+      const uint32_t base = tm + ((warp >> 2) & 1) * 128;
+      ld_32x32b_x32(base, r0); ld_32x32b_x32(base + 32, r1); ld_32x32b_x32(base + 64, r2); ld_32x32b_x32(base + 96, r3);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc ^= r0[i] ^ r1[i] ^ r2[i] ^ r3[i];
+      continue;
+    }
     uint32_t r[32];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {   // 4 x (32 lanes x 32 columns x 4 B) = 16 KB per warp per iteration
@@ -65,10 +74,10 @@ int main() {
   const int iters = 2000;
   const char* names[3] = {"32x32b.x32 (4 KB/instr)", "16x256b.x8 (2 KB/instr, 16 lanes)", "16x128b.x16 (2 KB/instr, 16 lanes)"};
   for (int shape = 0; shape < 3; ++shape)
-    for (int warps = 4; warps <= 16; warps *= 2) {
-      if (shape == 0) k<0><<<148, warps * 32>>>(out, sink, iters);
-      if (shape == 1) k<1><<<148, warps * 32>>>(out, sink, iters);
-      if (shape == 2) k<2><<<148, warps * 32>>>(out, sink, iters);
+    for (int warps = 1; warps <= 16; warps *= 2) {
+      if (shape == 0) k<0, 0><<<148, warps * 32>>>(out, sink, iters);
+      if (shape == 1) k<1, 0><<<148, warps * 32>>>(out, sink, iters);
+      if (shape == 2) k<2, 0><<<148, warps * 32>>>(out, sink, iters);
       cudaError_t e = cudaDeviceSynchronize();
       unsigned long long h[148]; cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
       const double bytes_per_instr = (shape == 0) ? 4096.0 : 2048.0;
@@ -76,5 +85,14 @@ int main() {
       printf("%-36s warps=%2d: %8.1f cycles/iter  -> %6.1f B/clk/SM  (%s)\n", names[shape], warps, (double)h[0] / iters, bytes / (double)h[0],
              cudaGetErrorString(e));
     }
+  // warps 1, 2, 4 sit in different lane quarters (sub-partitions); 8 = two per quarter; 16 = four per quarter
+  for (int warps = 1; warps <= 16; warps *= 2) {
+    k<0, 1><<<148, warps * 32>>>(out, sink, iters);
+    cudaError_t e = cudaDeviceSynchronize();
+    unsigned long long h[148]; cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
+    const double bytes = (double)warps * iters * 4 * 4096.0;
+    printf("%-36s warps=%2d: %8.1f cycles/iter  -> %6.1f B/clk/SM  (%s)\n", "32x32b.x32, 4 in flight", warps, (double)h[0] / iters,
+           bytes / (double)h[0], cudaGetErrorString(e));
+  }
   return 0;
 }
