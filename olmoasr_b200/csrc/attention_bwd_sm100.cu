@@ -9,7 +9,8 @@
 //     P  = exp2(S c - LSE)  dS = P o (dP - D)                (thread r owns query row r: no reductions)
 //     dV += P^T dO          dK += dS^T Q        dQ_i = dS K  (P / dS go through swizzled smem as bf16;
 //                                                             the "transposes" are MN-major descriptors)
-// dV and dK stay resident in TMEM for the whole loop; dQ_i is drained per query tile into a swizzled fp32 smem tile
+// dV and dK stay resident in TMEM for the whole loop and leave through swizzled smem tiles + one TMA store each; dQ_i is
+// drained per query tile into a swizzled fp32 smem tile
 // and reduced across key tiles with ONE bulk TMA reduce-add per 32-column half (cp.reduce.async.bulk.tensor .add)
 // into an fp32 scratch buffer (converted to bf16 afterwards).  (Per-thread red.global.add.v4 made the whole kernel
 // atomics-bound: ~6500 cycles per tile pair against ~1300 of tensor work.)
@@ -39,22 +40,21 @@ constexpr int BWD_TILES = 2 * TILE_BYTES + Q_STAGES * 2 * TILE_BYTES + 2 * P_BYT
 constexpr int BWD_SMEM = BWD_TILES + 256;
 constexpr int TMEM_COLS = 512;
 constexpr int S_COL = 0, DP_COL = 128, DV_COL = 256, DK_COL = 320, DQ_COL = 384;
-#ifndef OASR_BWD_DRAIN_WG
-#define OASR_BWD_DRAIN_WG 1
+// Share of the exponentials of an unmasked tile evaluated on the FMA pipe (exp2_poly2) instead of MUFU.EX2:
+// 0 = none, 1 = every fourth pair, 2 = every second pair.
+// Measured (profiles/r02_attention_ab_pingpong_poly.txt): 1 = 1.154 ms, 0 = 1.178 ms, 2 = 1.242 ms on the encoder shape.
+#ifndef OASR_BWD_POLY
+#define OASR_BWD_POLY 1
 #endif
-constexpr bool DRAIN_WG = OASR_BWD_DRAIN_WG != 0;
-constexpr int BWD_THREADS = DRAIN_WG ? 512 : 384;
-// register pool: 8 * 184 + 4 * 96 + 4 * 48 == 16 * 128 (drain warpgroup)   |   8 * 184 + 4 * 136 == 12 * 168
-constexpr int COMPUTE_REGS = 184, CONTROL_REGS = DRAIN_WG ? 96 : 136, DRAIN_REGS = 48;
+constexpr int BWD_THREADS = 512;
+// register pool: 8 * 184 (compute) + 4 * 96 (TMA / MMA warpgroup) + 4 * 48 (drain) == 16 * 128
+constexpr int COMPUTE_REGS = 184, CONTROL_REGS = 96, DRAIN_REGS = 48;
 
 struct BwdParams {
   const float* lse;   // (B,H,Tq) log2 domain
   const float* delta; // (B,H,Tq) rowsum(dO o O)
   float* dq_accum;    // (B*Tq, H*64) fp32, zero-initialised
-  bf16* dk;
-  bf16* dv;
   const int32_t* kv_len;
-  int64_t lddk, lddv;
   int B, H, Tq, Tkv;
   int causal;
   float scale, scale_log2;
@@ -83,20 +83,6 @@ __device__ unsigned long long g_bwd_trace[4][512];
 #define TRACE_END()
 #endif
 
-__device__ __forceinline__ void store_swizzled_row32(uint32_t tile_base, int r, int cc, const float (&x)[32]) {
-  // 32 consecutive bf16 columns [cc*32, cc*32+32) of row r into a two-half [128][128B] swizzled tile
-  const uint32_t half_base = tile_base + (cc >> 1) * (P_BYTES / 2) + r * 128;
-#pragma unroll
-  for (int q4 = 0; q4 < 4; ++q4) {
-    const int chunk = (cc & 1) * 4 + q4;
-    const uint32_t addr = half_base + ((chunk ^ (r & 7)) << 4);
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
-                 "r"(pack_bf16x2(x[8 * q4 + 0], x[8 * q4 + 1])), "r"(pack_bf16x2(x[8 * q4 + 2], x[8 * q4 + 3])),
-                 "r"(pack_bf16x2(x[8 * q4 + 4], x[8 * q4 + 5])), "r"(pack_bf16x2(x[8 * q4 + 6], x[8 * q4 + 7]))
-                 : "memory");
-  }
-}
-
 // 512 threads: warps 0..7 compute (warp w: TMEM lane quarter w%4, key-column half w/4), warp 8 TMA producer,
 // warp 9 MMA issuer + TMEM owner, warps 10-11 idle, warps 12..15 dQ drain (lane quarter w%4).  setmaxnreg gives the
 // compute warps 184 registers so that a thread holds its 64 S and 64 dP values at once: both TMEM buffers are released
@@ -105,7 +91,8 @@ __device__ __forceinline__ void store_swizzled_row32(uint32_t tile_base, int r, 
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
-                     const __grid_constant__ CUtensorMap tmDQ, const BwdParams p) {
+                     const __grid_constant__ CUtensorMap tmDQ, const __grid_constant__ CUtensorMap tmDK,
+                     const __grid_constant__ CUtensorMap tmDV, const BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + BWD_TILES);
   uint64_t& bar_kv = bars[0];
@@ -140,7 +127,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
   if (warp == 8 && lane == 0) {
     ptx::tma_prefetch_desc(&tmQ); ptx::tma_prefetch_desc(&tmK); ptx::tma_prefetch_desc(&tmV); ptx::tma_prefetch_desc(&tmdO);
-    ptx::tma_prefetch_desc(&tmDQ);
+    ptx::tma_prefetch_desc(&tmDQ); ptx::tma_prefetch_desc(&tmDK); ptx::tma_prefetch_desc(&tmDV);
     ptx::mbar_init(ptx::smem_u32(&bar_kv), 1);
     ptx::mbar_init(ptx::smem_u32(&bar_sdp), 1);
     ptx::mbar_init(ptx::smem_u32(&bar_free), 8);
@@ -168,7 +155,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   ptx::tc_fence_after();
   const uint32_t tmem = tmem_slot;
 
-  if (DRAIN_WG && warp >= 12) {
+  if (warp >= 12) {
     ptx::setmaxnreg_dec<DRAIN_REGS>();
     // ------------------------------ dQ drain warpgroup ------------------------------
     // dQ of query tile `it`: TMEM (this warp's 32 lanes x 64 columns) -> swizzled fp32 smem rows (two 32-column halves of
@@ -295,7 +282,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           TR(7);
         }
         const uint32_t dob = doB_lo0 + st * STAGE_LO, qb = qB_lo0 + st * STAGE_LO;
-        ptx::mbar_wait(ptx::smem_u32(&bar_pds), it & 1);  // P, dS in smem (without the drain warpgroup: and dQ TMEM drained)
+        ptx::mbar_wait(ptx::smem_u32(&bar_pds), it & 1);  // P, dS in smem
         TR(8);
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
@@ -308,7 +295,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           }
         }
         __syncwarp();
-        if (DRAIN_WG && it > 0) {   // the drain warps have read dQ of the previous tile out of TMEM
+        if (it > 0) {   // the drain warps have read dQ of the previous tile out of TMEM
           ptx::mbar_wait(ptx::smem_u32(&bar_dqfree), (it - 1) & 1);
           ptx::tc_fence_after();
         }
@@ -343,40 +330,6 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #define TRC(id_)
 #endif
     TRC(1);
-
-    // dQ of query tile `it`: this warp's 32 of the 64 columns -> swizzled fp32 smem rows -> one TMA reduce-add per
-    // column half (128 threads = the 4 warps sharing `chalf` cooperate through named barrier 1 + chalf)
-    const uint32_t sDQh = sDQ + chalf * (DQ_BYTES / 2);
-    const bool issuer = (quarter == 0 && lane == 0);
-    auto drain_dq = [&](int it) {
-      ptx::mbar_wait(ptx::smem_u32(&bar_dq), it & 1);
-      TRC(20);
-      ptx::tc_fence_after();
-      uint32_t v[32];
-      ptx::tc_ld_32x32b_x32(tmem + t_lane + DQ_COL + chalf * 32, v);
-      ptx::tc_wait_ld();
-      ptx::tc_fence_before();
-      TRC(21);
-      if (issuer) ptx::tma_store_wait_read<0>();               // previous reduce has finished reading the staging tile
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + chalf) : "memory");
-      TRC(22);
-#pragma unroll
-      for (int q4 = 0; q4 < 8; ++q4) {
-        const uint32_t addr = sDQh + r * 128 + ((q4 ^ (r & 7)) << 4);
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(__uint_as_float(v[4 * q4]) * p.scale),
-                     "f"(__uint_as_float(v[4 * q4 + 1]) * p.scale), "f"(__uint_as_float(v[4 * q4 + 2]) * p.scale),
-                     "f"(__uint_as_float(v[4 * q4 + 3]) * p.scale)
-                     : "memory");
-      }
-      ptx::fence_proxy_async_smem();
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + chalf) : "memory");
-      TRC(23);
-      if (issuer) {
-        // rows past Tq carry exact zeros (their P and dS rows are zero), rows past the tensor are clipped by TMA
-        ptx::tma_reduce_add_2d(&tmDQ, sDQh, h * HD + chalf * 32, b * p.Tq + (i_begin + it) * BQ);
-        ptx::tma_store_commit();
-      }
-    };
 
     // lse / delta of this thread's query row are fetched one iteration ahead (their ~1 us global-load latency used to
     // be the top stall of the compute warps)
@@ -425,8 +378,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             const float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[hh * 32 + i]), __uint_as_float(sv[hh * 32 + i + 1])), c2, nl2);
-            // MUFU.EX2 for every element: ncu shows the XU pipe at 8 % while issue slots are the scarce resource here
-            float2 pe = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+            float2 pe;
+            if (!MASKED && ((OASR_BWD_POLY == 2 && ((i >> 1) & 1)) || (OASR_BWD_POLY == 1 && ((i >> 1) & 3) == 3))) pe = exp2_poly2(x);
+            else pe = make_float2(fast_exp2(x.x), fast_exp2(x.y));
             if (MASKED) {
               if (cc * 32 + i >= limit) pe.x = 0.f;
               if (cc * 32 + i + 1 >= limit) pe.y = 0.f;
@@ -440,10 +394,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       };
       if (__all_sync(0xffffffffu, limit >= (chalf + 1) * 64)) p_ds(std::false_type{}); else p_ds(std::true_type{});
       TRC(13);
-      if (it > 0) {   // dV/dK/dQ MMAs of the previous tile retired => sP / sdS reusable
-        if (DRAIN_WG) ptx::mbar_wait(ptx::smem_u32(&bar_dq), (it - 1) & 1);
-        else drain_dq(it - 1);
-      }
+      if (it > 0) ptx::mbar_wait(ptx::smem_u32(&bar_dq), (it - 1) & 1);   // dV/dK/dQ MMAs of the previous tile retired => sP / sdS reusable
       TRC(14);
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
@@ -464,21 +415,17 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_pds));
       TRC(15);
     }
-    if (!DRAIN_WG && n_iter > 0) {
-      drain_dq(n_iter - 1);
-      if (issuer) ptx::tma_store_wait_read<0>();
-    }
     TRC(30);
 
     // ---- dK / dV for key row r of this tile (this warp's 32 of the 64 columns)
-    const int ki = kv0 + r;
     if (n_iter > 0) {
       ptx::mbar_wait(ptx::smem_u32(&bar_done), 0);
       ptx::tc_fence_after();
     }
     TRC(31);
-    bf16* dk_row = p.dk + (static_cast<int64_t>(b) * p.Tkv + ki) * p.lddk + h * HD;
-    bf16* dv_row = p.dv + (static_cast<int64_t>(b) * p.Tkv + ki) * p.lddv + h * HD;
+    // dK / dV tile -> swizzled bf16 smem tiles (the P / dS buffers are free now) -> one TMA store each.  (Per-thread
+    // 16-byte global stores of 64-byte row pieces took ~3300 cycles at the end of every CTA and stalled the last dQ drain
+    // behind them in the LSU; profiles/r02_attention_bwd_trace_after.txt.)  The 3-D tensor maps clip rows past Tkv.
     {
       const int cc = chalf;
       uint32_t a[32], bq[32];
@@ -490,21 +437,25 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
         for (int i = 0; i < 32; ++i) { a[i] = 0u; bq[i] = 0u; }
       }
-      if (ki < p.Tkv) {
 #pragma unroll
-        for (int q8 = 0; q8 < 4; ++q8) {
-          uint4 u, w;
-          u.x = pack_bf16x2(__uint_as_float(a[8 * q8 + 0]), __uint_as_float(a[8 * q8 + 1]));
-          u.y = pack_bf16x2(__uint_as_float(a[8 * q8 + 2]), __uint_as_float(a[8 * q8 + 3]));
-          u.z = pack_bf16x2(__uint_as_float(a[8 * q8 + 4]), __uint_as_float(a[8 * q8 + 5]));
-          u.w = pack_bf16x2(__uint_as_float(a[8 * q8 + 6]), __uint_as_float(a[8 * q8 + 7]));
-          w.x = pack_bf16x2(__uint_as_float(bq[8 * q8 + 0]) * p.scale, __uint_as_float(bq[8 * q8 + 1]) * p.scale);
-          w.y = pack_bf16x2(__uint_as_float(bq[8 * q8 + 2]) * p.scale, __uint_as_float(bq[8 * q8 + 3]) * p.scale);
-          w.z = pack_bf16x2(__uint_as_float(bq[8 * q8 + 4]) * p.scale, __uint_as_float(bq[8 * q8 + 5]) * p.scale);
-          w.w = pack_bf16x2(__uint_as_float(bq[8 * q8 + 6]) * p.scale, __uint_as_float(bq[8 * q8 + 7]) * p.scale);
-          reinterpret_cast<uint4*>(dv_row + cc * 32)[q8] = u;
-          reinterpret_cast<uint4*>(dk_row + cc * 32)[q8] = w;
-        }
+      for (int q8 = 0; q8 < 4; ++q8) {
+        const uint32_t off = r * 128 + (((cc * 4 + q8) ^ (r & 7)) << 4);
+        ptx::st_shared_v4(sP + off, pack_bf16x2(__uint_as_float(a[8 * q8 + 0]), __uint_as_float(a[8 * q8 + 1])),
+                          pack_bf16x2(__uint_as_float(a[8 * q8 + 2]), __uint_as_float(a[8 * q8 + 3])),
+                          pack_bf16x2(__uint_as_float(a[8 * q8 + 4]), __uint_as_float(a[8 * q8 + 5])),
+                          pack_bf16x2(__uint_as_float(a[8 * q8 + 6]), __uint_as_float(a[8 * q8 + 7])));
+        ptx::st_shared_v4(sdS + off, pack_bf16x2(__uint_as_float(bq[8 * q8 + 0]) * p.scale, __uint_as_float(bq[8 * q8 + 1]) * p.scale),
+                          pack_bf16x2(__uint_as_float(bq[8 * q8 + 2]) * p.scale, __uint_as_float(bq[8 * q8 + 3]) * p.scale),
+                          pack_bf16x2(__uint_as_float(bq[8 * q8 + 4]) * p.scale, __uint_as_float(bq[8 * q8 + 5]) * p.scale),
+                          pack_bf16x2(__uint_as_float(bq[8 * q8 + 6]) * p.scale, __uint_as_float(bq[8 * q8 + 7]) * p.scale));
+      }
+      ptx::fence_proxy_async_smem();
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (threadIdx.x == 0) {
+        ptx::tma_store_3d(&tmDV, sP, h * HD, kv0, b);
+        ptx::tma_store_3d(&tmDK, sdS, h * HD, kv0, b);
+        ptx::tma_store_commit();
+        ptx::tma_store_wait_read<0>();   // the tiles stay valid until the engine has read them
       }
     }
     TRC(32);
@@ -588,13 +539,20 @@ extern "C" int oasr_attention_bwd(const void* q, int64_t ldq, const void* k, int
   OASR_REQUIRE(((ldq | ldk | ldv | ldo | lddo | lddq | lddk | lddv) & 7) == 0, "attention_bwd: strides must be multiples of 8");
   OASR_REQUIRE(!causal || Tq == Tkv, "attention_bwd: causal needs Tq == Tkv");
   cudaStream_t st = (cudaStream_t)stream;
-  CUtensorMap tmQ, tmK, tmV, tmdO, tmDQ;
+  CUtensorMap tmQ, tmK, tmV, tmdO, tmDQ, tmDK, tmDV;
   int rc;
   if ((rc = make_tmap_2d(&tmQ, q, 2, (uint64_t)(H * HD), (uint64_t)(B * Tq), (uint64_t)ldq * 2, HD, BQ, true))) return rc;
   if ((rc = make_tmap_2d(&tmK, k, 2, (uint64_t)(H * HD), (uint64_t)(B * Tkv), (uint64_t)ldk * 2, HD, BKV, true))) return rc;
   if ((rc = make_tmap_2d(&tmV, v, 2, (uint64_t)(H * HD), (uint64_t)(B * Tkv), (uint64_t)ldv * 2, HD, BKV, true))) return rc;
   if ((rc = make_tmap_2d(&tmdO, dout, 2, (uint64_t)(H * HD), (uint64_t)(B * Tq), (uint64_t)lddo * 2, HD, BQ, true))) return rc;
   if ((rc = make_tmap_2d(&tmDQ, dq_accum, 4, (uint64_t)(H * HD), (uint64_t)(B * Tq), (uint64_t)(H * HD) * 4, 32, BQ, true))) return rc;
+
+  // dK / dV are stored per (batch, key tile): 3-D maps (columns, keys of one sample, batch) so that the 128-row box of the
+  // last key tile is clipped at Tkv instead of running into the next sample
+  if ((rc = make_tmap_3d(&tmDK, dk, 2, (uint64_t)(H * HD), (uint64_t)Tkv, (uint64_t)B, (uint64_t)lddk * 2, (uint64_t)Tkv * lddk * 2, HD,
+                         BKV, 1, true))) return rc;
+  if ((rc = make_tmap_3d(&tmDV, dv, 2, (uint64_t)(H * HD), (uint64_t)Tkv, (uint64_t)B, (uint64_t)lddv * 2, (uint64_t)Tkv * lddv * 2, HD,
+                         BKV, 1, true))) return rc;
 
   const int64_t n_items = B * Tq * H;
   attention_delta_kernel<<<(unsigned)ceil_div(n_items * 8, 256), 256, 0, st>>>((const bf16*)o, (const bf16*)dout, delta, ldo, lddo,
@@ -603,8 +561,8 @@ extern "C" int oasr_attention_bwd(const void* q, int64_t ldq, const void* k, int
   OASR_CUDA_OK(cudaMemsetAsync(dq_accum, 0, sizeof(float) * B * Tq * H * HD, st));
 
   BwdParams p;
-  p.lse = lse; p.delta = delta; p.dq_accum = dq_accum; p.dk = (bf16*)dk; p.dv = (bf16*)dv; p.kv_len = kv_len;
-  p.lddk = lddk; p.lddv = lddv; p.B = (int)B; p.H = (int)H; p.Tq = (int)Tq; p.Tkv = (int)Tkv; p.causal = causal;
+  p.lse = lse; p.delta = delta; p.dq_accum = dq_accum; p.kv_len = kv_len;
+  p.B = (int)B; p.H = (int)H; p.Tq = (int)Tq; p.Tkv = (int)Tkv; p.causal = causal;
   p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
   static bool attr_set = false;
   if (!attr_set) {
@@ -612,7 +570,7 @@ extern "C" int oasr_attention_bwd(const void* q, int64_t ldq, const void* k, int
     attr_set = true;
   }
   dim3 grid((unsigned)ceil_div(Tkv, BKV), (unsigned)H, (unsigned)B);
-  attention_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, st>>>(tmQ, tmK, tmV, tmdO, tmDQ, p);
+  attention_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, st>>>(tmQ, tmK, tmV, tmdO, tmDQ, tmDK, tmDV, p);
   OASR_LAUNCH_CHECK();
   const int64_t rows = B * Tq;
   int64_t blocks = ceil_div(rows * (H * HD / 8), 256);

@@ -45,6 +45,13 @@ constexpr int P_BYTES = BQ * BKV * 2;        // 32 KB: two 64-key halves of [128
 #define OASR_FWD_P_TMEM 0
 #endif
 constexpr bool P_TMEM = OASR_FWD_P_TMEM != 0;
+// The two softmax warpgroups share the SM's MUFU units.  1 = they take turns in the exponential phase (named barriers
+// 2 / 3, the FlashAttention-3 "ping-pong"): one warpgroup's TMEM reads / row maximum / O rescale then run under the
+// other's exponentials instead of both idling the MUFU pipe at the same time.
+#ifndef OASR_FWD_PINGPONG
+#define OASR_FWD_PINGPONG 0
+#endif
+constexpr bool PINGPONG = OASR_FWD_PINGPONG != 0;
 constexpr int ATT_TILES = 2 * TILE_BYTES /*Q0,Q1*/ + KV_STAGES * 2 * TILE_BYTES /*K,V*/ + (P_TMEM ? 0 : 2 * P_BYTES);  // 128 / 192 KB
 constexpr int ATT_SMEM = ATT_TILES + 256;
 constexpr int TMEM_COLS = 512;
@@ -55,6 +62,28 @@ constexpr int SOFTMAX_REGS = 224, CONTROL_REGS = 56;   // 8 * SOFTMAX + 4 * CONT
 // 0 = none, 1 = every fourth pair (25 %), 2 = every second pair (50 %).  A/B builds: python -m olmoasr_b200.build --variant.
 #ifndef OASR_ATTN_POLY
 #define OASR_ATTN_POLY 0
+#endif
+
+#ifdef OASR_ATTN_TRACE
+// Debug build only: one CTA in the middle of the grid stamps clock64() at phase boundaries (tools/trace_attention.py).
+__device__ unsigned long long g_fwd_trace[4][512];
+#define TRACE_DECL(role_)                                                                                     \
+  const bool tr_on = (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) == (gridDim.x * gridDim.y * gridDim.z) / 2 + gridDim.x / 2 && \
+                     lane == 0 && (role_) >= 0;                                                               \
+  const int tr_role = (role_) < 0 ? 0 : (role_);                                                              \
+  int tr_n = 0;
+#define TR(id_)                                                                                               \
+  do {                                                                                                        \
+    if (tr_on && tr_n < 511) g_fwd_trace[tr_role][++tr_n] = (static_cast<unsigned long long>(id_) << 48) | (clock64() & 0xffffffffffffull); \
+  } while (0)
+#define TRACE_END()                                                                                           \
+  do {                                                                                                        \
+    if (tr_on) g_fwd_trace[tr_role][0] = tr_n;                                                                \
+  } while (0)
+#else
+#define TRACE_DECL(role_)
+#define TR(id_)
+#define TRACE_END()
 #endif
 
 struct AttnParams {
@@ -148,6 +177,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
     } else if (warp == 9 && n_max > 0) {
       // ------------------------------ MMA issuer (whole warp convergent; elect.sync picks the issuing lane) ------------------------------
+      TRACE_DECL(1)
+      TR(1);
       constexpr uint32_t idesc_qk = ptx::umma_idesc_bf16(BQ, BKV, 0, 0);
       constexpr uint32_t idesc_pv = ptx::umma_idesc_bf16(BQ, HD, 0, 1);
       uint32_t q_lo[2], p_lo[2], k_lo0, v_lo0, hi_k, hi_v, unused;
@@ -190,6 +221,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
       for (int t = 0; t < 2; ++t)
         if (n_kv[t] > 0) issue_qk(t, 0);
+      TR(2);
       int st = 0;            // ring stage of key tile j
       uint32_t st_ph = 0;    // its phase
       for (int j = 0; j < n_max; ++j) {
@@ -199,12 +231,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         // (1) next tile's scores as soon as this tile's S has been read into registers
         if (j + 1 < n_max) {
           ptx::mbar_wait(ptx::smem_u32(&bar_kv_full[st_n]), ph_n);
+          TR(3);
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             if (j + 1 < n_kv[t]) {
               ptx::mbar_wait(ptx::smem_u32(&bar_sfree[t]), j & 1);
+              TR(4 + 2 * t);
               ptx::tc_fence_after();
               issue_qk(t, st_n);
+              TR(5 + 2 * t);
             }
           }
         }
@@ -213,14 +248,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int t = 0; t < 2; ++t) {
           if (j < n_kv[t]) {
             ptx::mbar_wait(ptx::smem_u32(&bar_p[t]), j & 1);   // P_t(j) in smem, O_t rescaled
+            TR(8 + 2 * t);
             ptx::tc_fence_after();
             issue_pv(t, st, j);
+            TR(9 + 2 * t);
           }
         }
         if (ptx::elect_one()) ptx::tc_commit(ptx::smem_u32(&bar_kv_empty[st]));   // K/V stage free once every MMA issued so far retires
         __syncwarp();
         st = st_n; st_ph = ph_n;
       }
+      TRACE_END();
     }
   } else {
     // ----------------------------- softmax / output warpgroups -----------------------------
@@ -236,10 +274,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const uint32_t t_p = tmem + t_lane + P_COL + t * (BKV / 2);
     const float c = p.scale_log2;
     const int n_t = n_kv[t];
+    const int n_common = min(n_kv[0], n_kv[1]);      // key tiles on which both warpgroups work: turns are taken there
     float m = -INFINITY, l = 0.f;
+    TRACE_DECL(warp == 0 ? 0 : (warp == 4 ? 3 : -1))
+    TR(1);
+    if (PINGPONG && t == 1 && n_common > 0) asm volatile("bar.arrive 2, 256;" ::: "memory");   // warpgroup 0 goes first
 
     for (int j = 0; j < n_t; ++j) {
+      TR(10);
       ptx::mbar_wait(ptx::smem_u32(&bar_s[t]), j & 1);
+      TR(11);
       ptx::tc_fence_after();
       float v[BKV];
       {
@@ -252,6 +296,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_sfree[t]));   // S_t may be overwritten by Q K^T (j+1)
+      TR(12);
 
       const int k0 = j * BKV;
       int limit = kv_valid - k0;                     // keys [0, limit) of this tile are visible
@@ -273,8 +318,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const float m_new = fmaxf(m, mx);
       const bool need = (j == 0) || ((m_new - m) * c > RESCALE_LOG2);
       const float m_next = need ? m_new : m;
+      TR(13);
       if (j > 0) {
         ptx::mbar_wait(ptx::smem_u32(&bar_pv[t]), (j - 1) & 1);   // P_t V (j-1) retired: O_t valid, sP_t reusable
+        TR(14);
         ptx::tc_fence_after();
         if (__any_sync(0xffffffffu, need)) {
           const float alpha = need ? fast_exp2((m - m_next) * c) : 1.0f;
@@ -292,6 +339,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
       }
       m = m_next;
+      TR(15);
       // p = 2^(s*c - m*c) (packed FFMA2), row sum (FADD2), bf16 -> swizzled smem (A operand of P V)
       const float neg = (m == -INFINITY) ? 0.f : -m * c;
       const float2 c2 = make_float2(c, c), n2 = make_float2(neg, neg);
@@ -334,13 +382,22 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       // ncu of the MUFU-only build (profiles/r01_ncu_kernel_metrics.txt): XU pipe 59.5 %, issue slots 36.7 %, tensor
       // pipe 29.7 % -- 128 x 128 ex2 per tile at 16 / clk / SM is twice the tile's MMA time, so a share of the
       // exponentials moves to the FMA pipe (OASR_ATTN_POLY; measured per build in profiles/r02_attention_poly_ab.txt)
+      if (PINGPONG && j < n_common) {
+        if (t == 0) asm volatile("bar.sync 2, 256;" ::: "memory");
+        else asm volatile("bar.sync 3, 256;" ::: "memory");
+      }
       // (warp-uniform choice: with P_TMEM both paths contain .sync.aligned tcgen05.st)
       if (OASR_ATTN_POLY != 0 && __all_sync(0xffffffffu, limit >= BKV)) emit_p(std::integral_constant<int, OASR_ATTN_POLY>{});
       else emit_p(std::integral_constant<int, 0>{});
+      if (PINGPONG) {
+        if (t == 0 && j < n_common) asm volatile("bar.arrive 3, 256;" ::: "memory");
+        if (t == 1 && j + 1 < n_common) asm volatile("bar.arrive 2, 256;" ::: "memory");
+      }
       if (!P_TMEM) ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_p[t]));
+      TR(16);
       l += ((sums[0].x + sums[0].y) + (sums[1].x + sums[1].y)) + ((sums[2].x + sums[2].y) + (sums[3].x + sums[3].y));
     }
     if (n_t > 0) {
@@ -367,6 +424,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
       if (qi < p.Tq && p.lse) p.lse[(static_cast<int64_t>(b) * p.H + h) * p.Tq + qi] = m * c + log2f(l);
     }
+    TR(30);
+    TRACE_END();
   }
 
   ptx::tc_fence_before();
@@ -381,6 +440,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 }  // namespace oasr
 
 using namespace oasr;
+
+#ifdef OASR_ATTN_TRACE
+extern "C" OASR_API int oasr_debug_fwd_trace(unsigned long long* host_out) {   // 4 x 512 words
+  return cudaMemcpyFromSymbol(host_out, g_fwd_trace, sizeof(unsigned long long) * 4 * 512) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 extern "C" int oasr_attention_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                                   void* o, int64_t ldo, float* lse, int64_t B, int64_t H, int64_t Tq, int64_t Tkv,

@@ -97,6 +97,11 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t smem_src, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t smem_src,
                                                   int32_t c0, int32_t c1) {
   asm volatile(

@@ -22,6 +22,34 @@ NAMES = {
     2: {1: "start", 2: "stage free"},
 }
 NAMES[3] = {20: "dQ MMAs retired", 21: "dQ staged in smem", 22: "reduce-add issued"}
+# forward: roles 0 / 3 = softmax warps 0 / 4 (query tiles 0 / 1), 1 = MMA warp
+FWD = {
+    0: {1: "start", 10: "loop top", 11: "S ready", 12: "S in regs", 13: "row max done", 14: " P V(j-1) retired", 15: "O rescaled", 16: "P stored",
+        30: "O written"},
+    1: {1: "start", 2: "QK(0) issued", 3: "K,V(next) landed", 4: "S0 regs free", 5: "QK0(next) issued", 6: "S1 regs free", 7: "QK1(next) issued",
+        8: "P0 ready", 9: "PV0 issued", 10: "P1 ready", 11: "PV1 issued"},
+    2: {},
+}
+FWD[3] = FWD[0]
+
+
+def dump(fn, names):
+    buf = (ctypes.c_ulonglong * (4 * 512))()
+    assert fn(buf) == 0
+    ev = {}
+    for role in range(4):
+        n = buf[role * 512]
+        ev[role] = [((buf[role * 512 + 1 + i] >> 48), buf[role * 512 + 1 + i] & ((1 << 48) - 1)) for i in range(n)]
+    t0 = min(e[0][1] for e in ev.values() if e)
+    for role in (0, 1, 2, 3):
+        if not ev[role]:
+            continue
+        print(f"-- role {role}")
+        prev = None
+        for eid, t in ev[role]:
+            print(f"   {names[role].get(eid, eid):24s} +{(t - prev) if prev is not None else 0:6d}   @{t - t0:7d}")
+            prev = t
+
 
 B, H = 32, 16
 d = H * 64
@@ -36,17 +64,7 @@ for name, Tq, Tkv, causal in (("encoder self", 1500, 1500, False), ("cross", 448
     for _ in range(3):
         K.attention_bwd(q, k, v, o, dout, lse, B, H, Tq, Tkv, causal=causal, kv_len=None)
     torch.cuda.synchronize()
-    buf = (ctypes.c_ulonglong * (4 * 512))()
-    assert lib.oasr_debug_bwd_trace(buf) == 0
-    ev = {}
-    for role in range(4):
-        n = buf[role * 512]
-        ev[role] = [((buf[role * 512 + 1 + i] >> 48), buf[role * 512 + 1 + i] & ((1 << 48) - 1)) for i in range(n)]
-    t0 = min(e[0][1] for e in ev.values() if e)
-    print(f"==== {name}: Tq {Tq} Tkv {Tkv}")
-    for role in (0, 1, 2, 3):
-        print(f"-- role {role}")
-        prev = None
-        for eid, t in ev[role]:
-            print(f"   {NAMES[role].get(eid, eid):24s} +{(t - prev) if prev is not None else 0:6d}   @{t - t0:7d}")
-            prev = t
+    print(f"==== backward {name}: Tq {Tq} Tkv {Tkv}")
+    dump(lib.oasr_debug_bwd_trace, NAMES)
+    print(f"==== forward {name}: Tq {Tq} Tkv {Tkv}")
+    dump(lib.oasr_debug_fwd_trace, FWD)
