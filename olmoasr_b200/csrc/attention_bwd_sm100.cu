@@ -65,8 +65,7 @@ struct BwdParams {
 // grid stamps clock64() at every phase boundary; tools/trace_attention.py prints the per-phase cycle table.
 __device__ unsigned long long g_bwd_trace[4][512];
 #define TRACE_DECL(role_)                                                                                     \
-  const bool tr_on = (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) == (gridDim.x * gridDim.y * gridDim.z) / 2 + gridDim.x / 2 && \
-                     lane == 0;                                                                               \
+  const bool tr_on = blockIdx.x == gridDim.x / 2 && lane == 0;                                                                               \
   const int tr_role = (role_);                                                                                \
   int tr_n = 0;
 #define TR(id_)                                                                                               \
@@ -88,23 +87,50 @@ __device__ unsigned long long g_bwd_trace[4][512];
 // compute warps 184 registers so that a thread holds its 64 S and 64 dP values at once: both TMEM buffers are released
 // right after the load (bar_free) and the MMA warp issues S / dP of the NEXT query tile underneath this tile's exp / dS
 // math.
+//
+// Persistent: a CTA walks over work items (key tile, head, sample) with stride gridDim.x.  Setting a CTA up (barriers,
+// TMEM allocation, first K/V/Q loads: ~2900 cycles) and tearing it down (~4200 cycles after the last P / dS store) cost
+// 16 % of the encoder shape and 35 % of the cross-attention shape when every item was its own CTA
+// (profiles/r02_attention_trace_after_epilogue.txt); now the next item's K / V / Q loads and first S / dP MMAs run
+// under the current item's dK / dV epilogue.  mbarrier parities: per query-tile barriers follow g (iterations done by
+// this CTA), per item barriers follow w (items with work) or e (epilogues), so every role derives them the same way.
+struct Item {
+  int kv_tile, h, b, kv0, kv_valid, i_begin, n_iter;
+};
+
+__device__ __forceinline__ Item decode_item(const BwdParams& p, int id, int n_kv_tiles, int n_q_tiles) {
+  Item w;
+  const int rest = id / n_kv_tiles;
+  w.kv_tile = (id + rest) % n_kv_tiles;   // rotate the key tile per (head, sample): causal tiles cost 1 .. n_q_tiles iterations
+  w.h = rest % p.H;
+  w.b = rest / p.H;
+  w.kv0 = w.kv_tile * BKV;
+  w.kv_valid = p.Tkv;
+  if (p.kv_len) w.kv_valid = min(w.kv_valid, max(1, p.kv_len[w.b]));
+  w.i_begin = p.causal ? w.kv_tile : 0;
+  w.n_iter = (w.kv0 < w.kv_valid) ? n_q_tiles - w.i_begin : 0;   // fully masked key tile: no work, zero gradients
+  return w;
+}
+
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                      const __grid_constant__ CUtensorMap tmDQ, const __grid_constant__ CUtensorMap tmDK,
-                     const __grid_constant__ CUtensorMap tmDV, const BwdParams p) {
+                     const __grid_constant__ CUtensorMap tmDV, const BwdParams p, const int n_items) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + BWD_TILES);
-  uint64_t& bar_kv = bars[0];
-  uint64_t& bar_sdp = bars[1];    // S, dP ready (MMA commit)
-  uint64_t& bar_free = bars[2];   // S, dP read into registers (8 warp arrivals)
-  uint64_t& bar_pds = bars[3];    // P, dS in smem (8 warp arrivals)
-  uint64_t& bar_dq = bars[4];     // dV / dK / dQ MMAs of this tile retired (MMA commit)
-  uint64_t& bar_done = bars[5];
+  uint64_t& bar_kv = bars[0];      // K, V of an item landed                       (parity w)
+  uint64_t& bar_sdp = bars[1];     // S, dP ready (MMA commit)                      (parity g)
+  uint64_t& bar_free = bars[2];    // S, dP read into registers (8 warp arrivals)   (parity g)
+  uint64_t& bar_pds = bars[3];     // P, dS in smem (8 warp arrivals)               (parity g)
+  uint64_t& bar_dq = bars[4];      // dV / dK / dQ MMAs of this tile retired        (parity g)
+  uint64_t& bar_done = bars[5];    // every MMA of the item retired: dK / dV final, K / V smem free   (parity w)
   uint64_t* bar_q_full = bars + 6;
   uint64_t* bar_q_empty = bars + 6 + Q_STAGES;
-  uint64_t& bar_dqfree = bars[6 + 2 * Q_STAGES];   // dQ of the previous tile read out of TMEM (4 drain-warp arrivals)
-  uint32_t& tmem_slot = *reinterpret_cast<uint32_t*>(bars + 7 + 2 * Q_STAGES);
+  uint64_t& bar_dqfree = bars[6 + 2 * Q_STAGES];    // dQ read out of TMEM (4 drain-warp arrivals)           (parity g)
+  uint64_t& bar_accfree = bars[7 + 2 * Q_STAGES];   // dK / dV read out of TMEM (8 warp arrivals)            (parity w)
+  uint64_t& bar_epi = bars[8 + 2 * Q_STAGES];       // dK / dV staging tiles read by the TMA engine          (parity e)
+  uint32_t& tmem_slot = *reinterpret_cast<uint32_t*>(bars + 9 + 2 * Q_STAGES);
 
   const uint32_t sbase = ptx::smem_u32(smem_raw);
   if ((sbase & 1023u) != 0) {
@@ -115,15 +141,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const uint32_t sQ0 = sV + TILE_BYTES;            // stage s: Q at sQ0 + s*32K, dO right after
   const uint32_t sP = sQ0 + Q_STAGES * 2 * TILE_BYTES, sdS = sP + P_BYTES, sDQ = sdS + P_BYTES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kv_tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int kv0 = kv_tile * BKV;
-
-  int kv_valid = p.Tkv;
-  if (p.kv_len) kv_valid = min(kv_valid, max(1, p.kv_len[b]));
+  const int n_kv_tiles = (p.Tkv + BKV - 1) / BKV;
   const int n_q_tiles = (p.Tq + BQ - 1) / BQ;
-  const int i_begin = p.causal ? kv_tile : 0;
-  const int i_end = (kv0 < kv_valid) ? n_q_tiles : i_begin;  // fully masked key tile: no work, zero grads
-  const int n_iter = i_end - i_begin;
+  const int item0 = blockIdx.x, item_step = gridDim.x;
 
   if (warp == 8 && lane == 0) {
     ptx::tma_prefetch_desc(&tmQ); ptx::tma_prefetch_desc(&tmK); ptx::tma_prefetch_desc(&tmV); ptx::tma_prefetch_desc(&tmdO);
@@ -135,16 +155,13 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     ptx::mbar_init(ptx::smem_u32(&bar_dq), 1);
     ptx::mbar_init(ptx::smem_u32(&bar_done), 1);
     ptx::mbar_init(ptx::smem_u32(&bar_dqfree), 4);
+    ptx::mbar_init(ptx::smem_u32(&bar_accfree), 8);
+    ptx::mbar_init(ptx::smem_u32(&bar_epi), 1);
     for (int s = 0; s < Q_STAGES; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bar_q_full[s]), 1);
       ptx::mbar_init(ptx::smem_u32(&bar_q_empty[s]), 1);
     }
     ptx::fence_barrier_init();
-    if (n_iter > 0) {   // K / V are on their way while the CTA is still setting up (TMEM allocation, __syncthreads)
-      ptx::mbar_arrive_expect_tx(ptx::smem_u32(&bar_kv), 2 * TILE_BYTES);
-      ptx::tma_load_2d(sK, &tmK, ptx::smem_u32(&bar_kv), h * HD, b * p.Tkv + kv0);
-      ptx::tma_load_2d(sV, &tmV, ptx::smem_u32(&bar_kv), h * HD, b * p.Tkv + kv0);
-    }
   }
   if (warp == 9) {
     ptx::tmem_alloc<TMEM_COLS>(ptx::smem_u32(&tmem_slot));
@@ -158,7 +175,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   if (warp >= 12) {
     ptx::setmaxnreg_dec<DRAIN_REGS>();
     // ------------------------------ dQ drain warpgroup ------------------------------
-    // dQ of query tile `it`: TMEM (this warp's 32 lanes x 64 columns) -> swizzled fp32 smem rows (two 32-column halves of
+    // dQ of a query tile: TMEM (this warp's 32 lanes x 64 columns) -> swizzled fp32 smem rows (two 32-column halves of
     // [128][128 B]) -> one TMA reduce-add per half into the fp32 scratch.  Rows past Tq carry exact zeros (their P and dS
     // rows are zero), rows past the tensor are clipped by TMA.
     TRACE_DECL(3)
@@ -166,65 +183,78 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int r = quarter * 32 + lane;
     const uint32_t t_lane = static_cast<uint32_t>(quarter * 32) << 16;
     const bool issuer = (warp == 12 && lane == 0);
-    for (int it = 0; it < n_iter; ++it) {
-      ptx::mbar_wait(ptx::smem_u32(&bar_dq), it & 1);
-      TR(20);
-      ptx::tc_fence_after();
-      if (issuer) ptx::tma_store_wait_read<0>();   // the previous reduce has finished reading the staging tile
+    uint32_t g = 0;
+    for (int id = item0; id < n_items; id += item_step) {
+      const Item w = decode_item(p, id, n_kv_tiles, n_q_tiles);
+      for (int it = 0; it < w.n_iter; ++it, ++g) {
+        ptx::mbar_wait(ptx::smem_u32(&bar_dq), g & 1);
+        TR(20);
+        ptx::tc_fence_after();
+        if (issuer) ptx::tma_store_wait_read<0>();   // the previous reduce has finished reading the staging tile
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t v[32];
-        ptx::tc_ld_32x32b_x32(tmem + t_lane + DQ_COL + half * 32, v);
-        ptx::tc_wait_ld();
-        if (half == 1) {
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_dqfree));   // dQ TMEM may be overwritten
-        } else {
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-        }
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v[32];
+          ptx::tc_ld_32x32b_x32(tmem + t_lane + DQ_COL + half * 32, v);
+          ptx::tc_wait_ld();
+          if (half == 1) {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_dqfree));   // dQ TMEM may be overwritten
+          } else {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+          }
 #pragma unroll
-        for (int q4 = 0; q4 < 8; ++q4) {
-          const uint32_t addr = sDQ + half * (DQ_BYTES / 2) + r * 128 + ((q4 ^ (r & 7)) << 4);
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(__uint_as_float(v[4 * q4]) * p.scale),
-                       "f"(__uint_as_float(v[4 * q4 + 1]) * p.scale), "f"(__uint_as_float(v[4 * q4 + 2]) * p.scale),
-                       "f"(__uint_as_float(v[4 * q4 + 3]) * p.scale)
-                       : "memory");
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const uint32_t addr = sDQ + half * (DQ_BYTES / 2) + r * 128 + ((q4 ^ (r & 7)) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(__uint_as_float(v[4 * q4]) * p.scale),
+                         "f"(__uint_as_float(v[4 * q4 + 1]) * p.scale), "f"(__uint_as_float(v[4 * q4 + 2]) * p.scale),
+                         "f"(__uint_as_float(v[4 * q4 + 3]) * p.scale)
+                         : "memory");
+          }
         }
+        TR(21);
+        ptx::fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (issuer) {
+          const int qrow = w.b * p.Tq + (w.i_begin + it) * BQ;
+          ptx::tma_reduce_add_2d(&tmDQ, sDQ, w.h * HD, qrow);
+          ptx::tma_reduce_add_2d(&tmDQ, sDQ + DQ_BYTES / 2, w.h * HD + 32, qrow);
+          ptx::tma_store_commit();
+        }
+        TR(22);
       }
-      TR(21);
-      ptx::fence_proxy_async_smem();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (issuer) {
-        const int qrow = b * p.Tq + (i_begin + it) * BQ;
-        ptx::tma_reduce_add_2d(&tmDQ, sDQ, h * HD, qrow);
-        ptx::tma_reduce_add_2d(&tmDQ, sDQ + DQ_BYTES / 2, h * HD + 32, qrow);
-        ptx::tma_store_commit();
-      }
-      TR(22);
     }
     if (issuer) ptx::tma_store_wait_read<0>();
     TRACE_END();
   } else if (warp >= 8) {
     ptx::setmaxnreg_dec<CONTROL_REGS>();
-    if (warp == 8 && lane == 0 && n_iter > 0) {
+    if (warp == 8 && lane == 0) {
       // ------------------------------ TMA producer ------------------------------
       TRACE_DECL(2)
       TR(1);
       int s = 0;
-      uint32_t ph = 0;
-      for (int it = 0; it < n_iter; ++it) {
-        ptx::mbar_wait(ptx::smem_u32(&bar_q_empty[s]), ph ^ 1);
-        TR(2);
-        const uint32_t full = ptx::smem_u32(&bar_q_full[s]);
-        ptx::mbar_arrive_expect_tx(full, 2 * TILE_BYTES);
-        const int qrow = b * p.Tq + (i_begin + it) * BQ;
-        ptx::tma_load_2d(sQ0 + s * 2 * TILE_BYTES, &tmQ, full, h * HD, qrow);
-        ptx::tma_load_2d(sQ0 + s * 2 * TILE_BYTES + TILE_BYTES, &tmdO, full, h * HD, qrow);
-        if (++s == Q_STAGES) { s = 0; ph ^= 1; }
+      uint32_t ph = 0, wi = 0;
+      for (int id = item0; id < n_items; id += item_step) {
+        const Item w = decode_item(p, id, n_kv_tiles, n_q_tiles);
+        if (w.n_iter == 0) continue;
+        if (wi > 0) ptx::mbar_wait(ptx::smem_u32(&bar_done), (wi - 1) & 1);   // the previous item's MMAs no longer read K / V
+        ptx::mbar_arrive_expect_tx(ptx::smem_u32(&bar_kv), 2 * TILE_BYTES);
+        ptx::tma_load_2d(sK, &tmK, ptx::smem_u32(&bar_kv), w.h * HD, w.b * p.Tkv + w.kv0);
+        ptx::tma_load_2d(sV, &tmV, ptx::smem_u32(&bar_kv), w.h * HD, w.b * p.Tkv + w.kv0);
+        for (int it = 0; it < w.n_iter; ++it) {
+          ptx::mbar_wait(ptx::smem_u32(&bar_q_empty[s]), ph ^ 1);
+          TR(2);
+          const uint32_t full = ptx::smem_u32(&bar_q_full[s]);
+          ptx::mbar_arrive_expect_tx(full, 2 * TILE_BYTES);
+          const int qrow = w.b * p.Tq + (w.i_begin + it) * BQ;
+          ptx::tma_load_2d(sQ0 + s * 2 * TILE_BYTES, &tmQ, full, w.h * HD, qrow);
+          ptx::tma_load_2d(sQ0 + s * 2 * TILE_BYTES + TILE_BYTES, &tmdO, full, w.h * HD, qrow);
+          if (++s == Q_STAGES) { s = 0; ph ^= 1; }
+        }
+        ++wi;
       }
       TRACE_END();
-    } else if (warp == 9 && n_iter > 0) {
+    } else if (warp == 9) {
       // ------------------------------ MMA issuer (whole warp convergent; elect.sync picks the issuing lane) ------------------------------
       TRACE_DECL(1)
       TR(1);
@@ -259,58 +289,65 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
         __syncwarp();
       };
-      ptx::mbar_wait(ptx::smem_u32(&bar_kv), 0);
-      TR(2);
-      ptx::mbar_wait(ptx::smem_u32(&bar_q_full[0]), 0);
-      TR(3);
-      ptx::tc_fence_after();
-      issue_s_dp(0);
-      TR(4);
       int st = 0;
-      uint32_t st_ph = 0;
-      for (int it = 0; it < n_iter; ++it) {
-        int st_n = st + 1;
-        uint32_t ph_n = st_ph;
-        if (st_n == Q_STAGES) { st_n = 0; ph_n ^= 1; }
-        if (it + 1 < n_iter) {   // next tile's S / dP as soon as this tile's have been read into registers
-          ptx::mbar_wait(ptx::smem_u32(&bar_q_full[st_n]), ph_n);
-          TR(5);
-          ptx::mbar_wait(ptx::smem_u32(&bar_free), it & 1);
-          TR(6);
-          ptx::tc_fence_after();
-          issue_s_dp(st_n);
-          TR(7);
-        }
-        const uint32_t dob = doB_lo0 + st * STAGE_LO, qb = qB_lo0 + st * STAGE_LO;
-        ptx::mbar_wait(ptx::smem_u32(&bar_pds), it & 1);  // P, dS in smem
-        TR(8);
+      uint32_t st_ph = 0, g = 0, wi = 0;
+      for (int id = item0; id < n_items; id += item_step) {
+        const Item w = decode_item(p, id, n_kv_tiles, n_q_tiles);
+        if (w.n_iter == 0) continue;
+        ptx::mbar_wait(ptx::smem_u32(&bar_kv), wi & 1);
+        TR(2);
+        ptx::mbar_wait(ptx::smem_u32(&bar_q_full[st]), st_ph);
+        if (g > 0) ptx::mbar_wait(ptx::smem_u32(&bar_free), (g - 1) & 1);   // S / dP of the previous item's last tile are in registers
+        TR(3);
         ptx::tc_fence_after();
-        if (ptx::elect_one()) {
-#pragma unroll
-          for (int k = 0; k < BQ / 16; ++k) {  // reduction over the 128 query rows, 16 at a time
-            ptx::tc_mma_f16_lh(tmem + DV_COL, pT_lo + k * (2048 >> 4), hi_mnA, dob + k * (2048 >> 4), hi_mnB, idesc_kv,
-                               (it > 0 || k > 0) ? 1u : 0u);
-            ptx::tc_mma_f16_lh(tmem + DK_COL, dsT_lo + k * (2048 >> 4), hi_mnA, qb + k * (2048 >> 4), hi_mnB, idesc_kv,
-                               (it > 0 || k > 0) ? 1u : 0u);
+        issue_s_dp(st);
+        TR(4);
+        for (int it = 0; it < w.n_iter; ++it, ++g) {
+          int st_n = st + 1;
+          uint32_t ph_n = st_ph;
+          if (st_n == Q_STAGES) { st_n = 0; ph_n ^= 1; }
+          if (it + 1 < w.n_iter) {   // next tile's S / dP as soon as this tile's have been read into registers
+            ptx::mbar_wait(ptx::smem_u32(&bar_q_full[st_n]), ph_n);
+            TR(5);
+            ptx::mbar_wait(ptx::smem_u32(&bar_free), g & 1);
+            TR(6);
+            ptx::tc_fence_after();
+            issue_s_dp(st_n);
+            TR(7);
           }
-        }
-        __syncwarp();
-        if (it > 0) {   // the drain warps have read dQ of the previous tile out of TMEM
-          ptx::mbar_wait(ptx::smem_u32(&bar_dqfree), (it - 1) & 1);
+          const uint32_t dob = doB_lo0 + st * STAGE_LO, qb = qB_lo0 + st * STAGE_LO;
+          ptx::mbar_wait(ptx::smem_u32(&bar_pds), g & 1);  // P, dS in smem
+          if (it == 0 && wi > 0) ptx::mbar_wait(ptx::smem_u32(&bar_accfree), (wi - 1) & 1);   // previous dK / dV left TMEM
+          TR(8);
           ptx::tc_fence_after();
-        }
-        if (ptx::elect_one()) {
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BKV / 16; ++k)   // dQ_i = dS K : reduction over the 128 keys
-            ptx::tc_mma_f16_lh(tmem + DQ_COL, dsK_lo + (k >> 2) * ((P_BYTES / 2) >> 4) + (k & 3) * 2, hi_k,
-                               kB_lo + k * (2048 >> 4), hi_mnB, idesc_dq, k > 0);
-          ptx::tc_commit(ptx::smem_u32(&bar_dq));
-          ptx::tc_commit(ptx::smem_u32(&bar_q_empty[st]));
-          if (it + 1 == n_iter) ptx::tc_commit(ptx::smem_u32(&bar_done));
+            for (int k = 0; k < BQ / 16; ++k) {  // reduction over the 128 query rows, 16 at a time
+              ptx::tc_mma_f16_lh(tmem + DV_COL, pT_lo + k * (2048 >> 4), hi_mnA, dob + k * (2048 >> 4), hi_mnB, idesc_kv,
+                                 (it > 0 || k > 0) ? 1u : 0u);
+              ptx::tc_mma_f16_lh(tmem + DK_COL, dsT_lo + k * (2048 >> 4), hi_mnA, qb + k * (2048 >> 4), hi_mnB, idesc_kv,
+                                 (it > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+          __syncwarp();
+          if (g > 0) {   // the drain warps have read dQ of the previous tile out of TMEM
+            ptx::mbar_wait(ptx::smem_u32(&bar_dqfree), (g - 1) & 1);
+            ptx::tc_fence_after();
+          }
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int k = 0; k < BKV / 16; ++k)   // dQ_i = dS K : reduction over the 128 keys
+              ptx::tc_mma_f16_lh(tmem + DQ_COL, dsK_lo + (k >> 2) * ((P_BYTES / 2) >> 4) + (k & 3) * 2, hi_k,
+                                 kB_lo + k * (2048 >> 4), hi_mnB, idesc_dq, k > 0);
+            ptx::tc_commit(ptx::smem_u32(&bar_dq));
+            ptx::tc_commit(ptx::smem_u32(&bar_q_empty[st]));
+            if (it + 1 == w.n_iter) ptx::tc_commit(ptx::smem_u32(&bar_done));
+          }
+          __syncwarp();
+          TR(9);
+          st = st_n; st_ph = ph_n;
         }
-        __syncwarp();
-        TR(9);
-        st = st_n; st_ph = ph_n;
+        ++wi;
       }
       TRACE_END();
     }
@@ -331,115 +368,124 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #endif
     TRC(1);
 
-    // lse / delta of this thread's query row are fetched one iteration ahead (their ~1 us global-load latency used to
-    // be the top stall of the compute warps)
-    const int64_t stat_base = (static_cast<int64_t>(b) * p.H + h) * p.Tq;
-    auto load_stats = [&](int it, float& lse_o, float& dlt_o) {
-      const int qn = (i_begin + it) * BQ + r;
-      const bool ok = it < n_iter && qn < p.Tq;
-      lse_o = ok ? __ldg(p.lse + stat_base + qn) : 0.f;
-      dlt_o = ok ? __ldg(p.delta + stat_base + qn) : 0.f;
+    // lse / delta of this thread's query row are fetched one iteration ahead -- across item boundaries too (their ~1 us
+    // global-load latency used to be the top stall of the compute warps)
+    auto load_stats = [&](const Item& w, int it, float& lse_o, float& dlt_o) {
+      const int qn = (w.i_begin + it) * BQ + r;
+      const bool ok = it < w.n_iter && qn < p.Tq;
+      const int64_t at = (static_cast<int64_t>(w.b) * p.H + w.h) * p.Tq + qn;
+      lse_o = ok ? __ldg(p.lse + at) : 0.f;
+      dlt_o = ok ? __ldg(p.delta + at) : 0.f;
     };
+    uint32_t g = 0, wi = 0, e = 0;
+    Item w = decode_item(p, item0 < n_items ? item0 : 0, n_kv_tiles, n_q_tiles);
     float lse_nx, dlt_nx;
-    load_stats(0, lse_nx, dlt_nx);
-    for (int it = 0; it < n_iter; ++it) {
-      const int q0 = (i_begin + it) * BQ;
-      const int qi = q0 + r;
-      const bool q_ok = qi < p.Tq;
-      const float lse = lse_nx, dlt = dlt_nx;
-      load_stats(it + 1, lse_nx, dlt_nx);
-      int limit = kv_valid - kv0;                     // visible keys of this tile: [0, limit)
-      if (p.causal) limit = min(limit, qi - kv0 + 1);
-      if (!q_ok) limit = 0;
-      TRC(10);
-      ptx::mbar_wait(ptx::smem_u32(&bar_sdp), it & 1);
-      TRC(11);
-      ptx::tc_fence_after();
-      uint32_t sv[64], dv[64];
-      ptx::tc_ld_32x32b_x32(tmem + t_lane + S_COL + chalf * 64, reinterpret_cast<uint32_t (&)[32]>(sv[0]));
-      ptx::tc_ld_32x32b_x32(tmem + t_lane + S_COL + chalf * 64 + 32, reinterpret_cast<uint32_t (&)[32]>(sv[32]));
-      ptx::tc_ld_32x32b_x32(tmem + t_lane + DP_COL + chalf * 64, reinterpret_cast<uint32_t (&)[32]>(dv[0]));
-      ptx::tc_ld_32x32b_x32(tmem + t_lane + DP_COL + chalf * 64 + 32, reinterpret_cast<uint32_t (&)[32]>(dv[32]));
-      ptx::tc_wait_ld();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_free));   // S / dP TMEM may be overwritten
-      TRC(12);
-      // All the exp / dS math happens BEFORE waiting for the previous tile's dV/dK/dQ MMAs (which still read sP / sdS):
-      // the results wait in registers as packed bf16, so the compute warps never idle behind the tensor pipe.
-      const float2 c2 = make_float2(c, c), nl2 = make_float2(-lse, -lse), nd2 = make_float2(-dlt, -dlt);
-      uint32_t pp[32], dd[32];   // 64 columns each, packed bf16x2
-      // MASKED is decided per warp (warp-uniform branch): interior tiles run without any per-element predicate code
-      auto p_ds = [&](auto masked_tag) {
-        constexpr bool MASKED = decltype(masked_tag)::value;
+    load_stats(w, 0, lse_nx, dlt_nx);
+    for (int id = item0; id < n_items; id += item_step) {
+      for (int it = 0; it < w.n_iter; ++it, ++g) {
+        const int q0 = (w.i_begin + it) * BQ;
+        const int qi = q0 + r;
+        const bool q_ok = qi < p.Tq;
+        const float lse = lse_nx, dlt = dlt_nx;
+        load_stats(w, it + 1, lse_nx, dlt_nx);
+        int limit = w.kv_valid - w.kv0;                     // visible keys of this tile: [0, limit)
+        if (p.causal) limit = min(limit, qi - w.kv0 + 1);
+        if (!q_ok) limit = 0;
+        TRC(10);
+        ptx::mbar_wait(ptx::smem_u32(&bar_sdp), g & 1);
+        TRC(11);
+        ptx::tc_fence_after();
+        uint32_t sv[64], dv[64];
+        ptx::tc_ld_32x32b_x32(tmem + t_lane + S_COL + chalf * 64, reinterpret_cast<uint32_t (&)[32]>(sv[0]));
+        ptx::tc_ld_32x32b_x32(tmem + t_lane + S_COL + chalf * 64 + 32, reinterpret_cast<uint32_t (&)[32]>(sv[32]));
+        ptx::tc_ld_32x32b_x32(tmem + t_lane + DP_COL + chalf * 64, reinterpret_cast<uint32_t (&)[32]>(dv[0]));
+        ptx::tc_ld_32x32b_x32(tmem + t_lane + DP_COL + chalf * 64 + 32, reinterpret_cast<uint32_t (&)[32]>(dv[32]));
+        ptx::tc_wait_ld();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_free));   // S / dP TMEM may be overwritten
+        TRC(12);
+        // All the exp / dS math happens BEFORE waiting for the previous tile's dV/dK/dQ MMAs (which still read sP / sdS):
+        // the results wait in registers as packed bf16, so the compute warps never idle behind the tensor pipe.
+        const float2 c2 = make_float2(c, c), nl2 = make_float2(-lse, -lse), nd2 = make_float2(-dlt, -dlt);
+        uint32_t pp[32], dd[32];   // 64 columns each, packed bf16x2
+        // MASKED is decided per warp (warp-uniform branch): interior tiles run without any per-element predicate code
+        auto p_ds = [&](auto masked_tag) {
+          constexpr bool MASKED = decltype(masked_tag)::value;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int cc = chalf * 2 + hh;
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[hh * 32 + i]), __uint_as_float(sv[hh * 32 + i + 1])), c2, nl2);
+              float2 pe;
+              if (!MASKED && ((OASR_BWD_POLY == 2 && ((i >> 1) & 1)) || (OASR_BWD_POLY == 1 && ((i >> 1) & 3) == 3))) pe = exp2_poly2(x);
+              else pe = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+              if (MASKED) {
+                if (cc * 32 + i >= limit) pe.x = 0.f;
+                if (cc * 32 + i + 1 >= limit) pe.y = 0.f;
+              }
+              const float2 dq2 = __fadd2_rn(make_float2(__uint_as_float(dv[hh * 32 + i]), __uint_as_float(dv[hh * 32 + i + 1])), nd2);
+              const float2 dsv = __fmul2_rn(pe, dq2);
+              pp[hh * 16 + (i >> 1)] = pack_bf16x2(pe.x, pe.y);
+              dd[hh * 16 + (i >> 1)] = pack_bf16x2(dsv.x, dsv.y);
+            }
+          }
+        };
+        if (__all_sync(0xffffffffu, limit >= (chalf + 1) * 64)) p_ds(std::false_type{}); else p_ds(std::true_type{});
+        TRC(13);
+        // sP / sdS are free once the previous tile's dV/dK/dQ MMAs have retired and, on an item's first tile, once the TMA
+        // engine has read the previous item's dK / dV staging tiles out of them
+        if (g > 0) ptx::mbar_wait(ptx::smem_u32(&bar_dq), (g - 1) & 1);
+        if (it == 0 && e > 0) ptx::mbar_wait(ptx::smem_u32(&bar_epi), (e - 1) & 1);
+        TRC(14);
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           const int cc = chalf * 2 + hh;
+          const uint32_t off = (cc >> 1) * (P_BYTES / 2) + r * 128;
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float2 x = __ffma2_rn(make_float2(__uint_as_float(sv[hh * 32 + i]), __uint_as_float(sv[hh * 32 + i + 1])), c2, nl2);
-            float2 pe;
-            if (!MASKED && ((OASR_BWD_POLY == 2 && ((i >> 1) & 1)) || (OASR_BWD_POLY == 1 && ((i >> 1) & 3) == 3))) pe = exp2_poly2(x);
-            else pe = make_float2(fast_exp2(x.x), fast_exp2(x.y));
-            if (MASKED) {
-              if (cc * 32 + i >= limit) pe.x = 0.f;
-              if (cc * 32 + i + 1 >= limit) pe.y = 0.f;
-            }
-            const float2 dq2 = __fadd2_rn(make_float2(__uint_as_float(dv[hh * 32 + i]), __uint_as_float(dv[hh * 32 + i + 1])), nd2);
-            const float2 dsv = __fmul2_rn(pe, dq2);
-            pp[hh * 16 + (i >> 1)] = pack_bf16x2(pe.x, pe.y);
-            dd[hh * 16 + (i >> 1)] = pack_bf16x2(dsv.x, dsv.y);
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const uint32_t a = off + ((((cc & 1) * 4 + q4) ^ (r & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP + a), "r"(pp[hh * 16 + q4 * 4]), "r"(pp[hh * 16 + q4 * 4 + 1]),
+                         "r"(pp[hh * 16 + q4 * 4 + 2]), "r"(pp[hh * 16 + q4 * 4 + 3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdS + a), "r"(dd[hh * 16 + q4 * 4]), "r"(dd[hh * 16 + q4 * 4 + 1]),
+                         "r"(dd[hh * 16 + q4 * 4 + 2]), "r"(dd[hh * 16 + q4 * 4 + 3]) : "memory");
           }
         }
-      };
-      if (__all_sync(0xffffffffu, limit >= (chalf + 1) * 64)) p_ds(std::false_type{}); else p_ds(std::true_type{});
-      TRC(13);
-      if (it > 0) ptx::mbar_wait(ptx::smem_u32(&bar_dq), (it - 1) & 1);   // dV/dK/dQ MMAs of the previous tile retired => sP / sdS reusable
-      TRC(14);
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int cc = chalf * 2 + hh;
-        const uint32_t off = (cc >> 1) * (P_BYTES / 2) + r * 128;
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const uint32_t a = off + ((((cc & 1) * 4 + q4) ^ (r & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP + a), "r"(pp[hh * 16 + q4 * 4]), "r"(pp[hh * 16 + q4 * 4 + 1]),
-                       "r"(pp[hh * 16 + q4 * 4 + 2]), "r"(pp[hh * 16 + q4 * 4 + 3]) : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sdS + a), "r"(dd[hh * 16 + q4 * 4]), "r"(dd[hh * 16 + q4 * 4 + 1]),
-                       "r"(dd[hh * 16 + q4 * 4 + 2]), "r"(dd[hh * 16 + q4 * 4 + 3]) : "memory");
-        }
+        ptx::fence_proxy_async_smem();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_pds));
+        TRC(15);
       }
-      ptx::fence_proxy_async_smem();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_pds));
-      TRC(15);
-    }
-    TRC(30);
+      TRC(30);
+      const Item w_next = decode_item(p, id + item_step < n_items ? id + item_step : id, n_kv_tiles, n_q_tiles);
+      if (id + item_step < n_items) load_stats(w_next, 0, lse_nx, dlt_nx);
 
-    // ---- dK / dV for key row r of this tile (this warp's 32 of the 64 columns)
-    if (n_iter > 0) {
-      ptx::mbar_wait(ptx::smem_u32(&bar_done), 0);
-      ptx::tc_fence_after();
-    }
-    TRC(31);
-    // dK / dV tile -> swizzled bf16 smem tiles (the P / dS buffers are free now) -> one TMA store each.  (Per-thread
-    // 16-byte global stores of 64-byte row pieces took ~3300 cycles at the end of every CTA and stalled the last dQ drain
-    // behind them in the LSU; profiles/r02_attention_bwd_trace_after.txt.)  The 3-D tensor maps clip rows past Tkv.
-    {
-      const int cc = chalf;
+      // ---- dK / dV of the item: key row r of the tile, this warp's 32 of the 64 columns -> swizzled bf16 smem tiles (the
+      // P / dS buffers are free now) -> one TMA store each.  (Per-thread 16-byte global stores of 64-byte row pieces took
+      // ~3300 cycles and stalled the last dQ drain behind them in the LSU.)  The 3-D tensor maps clip rows past Tkv.
       uint32_t a[32], bq[32];
-      if (n_iter > 0) {
-        ptx::tc_ld_32x32b_x32(tmem + t_lane + DV_COL + cc * 32, a);
-        ptx::tc_ld_32x32b_x32(tmem + t_lane + DK_COL + cc * 32, bq);
+      if (w.n_iter > 0) {
+        ptx::mbar_wait(ptx::smem_u32(&bar_done), wi & 1);
+        ptx::tc_fence_after();
+        TRC(31);
+        ptx::tc_ld_32x32b_x32(tmem + t_lane + DV_COL + chalf * 32, a);
+        ptx::tc_ld_32x32b_x32(tmem + t_lane + DK_COL + chalf * 32, bq);
         ptx::tc_wait_ld();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bar_accfree));   // the next item may start accumulating dK / dV
+        ++wi;
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) { a[i] = 0u; bq[i] = 0u; }
+        // a fully masked item still has to wait for the staging tiles (no P / dS store did it above)
+        if (e > 0) ptx::mbar_wait(ptx::smem_u32(&bar_epi), (e - 1) & 1);
       }
 #pragma unroll
       for (int q8 = 0; q8 < 4; ++q8) {
-        const uint32_t off = r * 128 + (((cc * 4 + q8) ^ (r & 7)) << 4);
+        const uint32_t off = r * 128 + (((chalf * 4 + q8) ^ (r & 7)) << 4);
         ptx::st_shared_v4(sP + off, pack_bf16x2(__uint_as_float(a[8 * q8 + 0]), __uint_as_float(a[8 * q8 + 1])),
                           pack_bf16x2(__uint_as_float(a[8 * q8 + 2]), __uint_as_float(a[8 * q8 + 3])),
                           pack_bf16x2(__uint_as_float(a[8 * q8 + 4]), __uint_as_float(a[8 * q8 + 5])),
@@ -452,13 +498,16 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       ptx::fence_proxy_async_smem();
       asm volatile("bar.sync 2, 256;" ::: "memory");
       if (threadIdx.x == 0) {
-        ptx::tma_store_3d(&tmDV, sP, h * HD, kv0, b);
-        ptx::tma_store_3d(&tmDK, sdS, h * HD, kv0, b);
+        ptx::tma_store_3d(&tmDV, sP, w.h * HD, w.kv0, w.b);
+        ptx::tma_store_3d(&tmDK, sdS, w.h * HD, w.kv0, w.b);
         ptx::tma_store_commit();
         ptx::tma_store_wait_read<0>();   // the tiles stay valid until the engine has read them
+        ptx::mbar_arrive(ptx::smem_u32(&bar_epi));
       }
+      ++e;
+      TRC(32);
+      w = w_next;
     }
-    TRC(32);
 #ifdef OASR_ATTN_TRACE
     if (tr_keep) TRACE_END();
 #endif
@@ -569,8 +618,12 @@ extern "C" int oasr_attention_bwd(const void* q, int64_t ldq, const void* k, int
     OASR_CUDA_OK(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
     attr_set = true;
   }
-  dim3 grid((unsigned)ceil_div(Tkv, BKV), (unsigned)H, (unsigned)B);
-  attention_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, st>>>(tmQ, tmK, tmV, tmdO, tmDQ, tmDK, tmDV, p);
+  // one CTA per SM walking over (key tile, head, sample) items; OASR_BWD_PERSISTENT=0: one CTA per item (A/B)
+  const int64_t n_work = ceil_div(Tkv, BKV) * H * B;
+  OASR_REQUIRE(n_work < (int64_t(1) << 31), "attention_bwd: too many work items");
+  static const bool persistent = [] { const char* e = getenv("OASR_BWD_PERSISTENT"); return !(e && e[0] == '0'); }();
+  const unsigned grid = persistent ? (unsigned)(n_work < num_sms() ? n_work : num_sms()) : (unsigned)n_work;
+  attention_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, st>>>(tmQ, tmK, tmV, tmdO, tmDQ, tmDK, tmDV, p, (int)n_work);
   OASR_LAUNCH_CHECK();
   const int64_t rows = B * Tq;
   int64_t blocks = ceil_div(rows * (H * HD / 8), 256);
