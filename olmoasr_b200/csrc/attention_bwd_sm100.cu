@@ -250,6 +250,21 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           ptx::tma_load_2d(sQ0 + s * 2 * TILE_BYTES, &tmQ, full, w.h * HD, qrow);
           ptx::tma_load_2d(sQ0 + s * 2 * TILE_BYTES + TILE_BYTES, &tmdO, full, w.h * HD, qrow);
           if (++s == Q_STAGES) { s = 0; ph ^= 1; }
+          if (it + 1 == w.n_iter) {
+            // K / V of the next item can only be loaded once this item's MMAs have retired; measured 3000+ cycles from
+            // that load to its arrival while the epilogue traffic is in flight (profiles/r02_attention_trace_persistent.txt).
+            // Pull the tiles into L2 now, one query tile ahead.
+            for (int nid = id + item_step; nid < n_items; nid += item_step) {
+              const Item nx = decode_item(p, nid, n_kv_tiles, n_q_tiles);
+              if (nx.n_iter == 0) continue;
+              ptx::tma_prefetch_l2_2d(&tmK, nx.h * HD, nx.b * p.Tkv + nx.kv0);
+              ptx::tma_prefetch_l2_2d(&tmV, nx.h * HD, nx.b * p.Tkv + nx.kv0);
+              const int qrow = nx.b * p.Tq + nx.i_begin * BQ;
+              ptx::tma_prefetch_l2_2d(&tmQ, nx.h * HD, qrow);
+              ptx::tma_prefetch_l2_2d(&tmdO, nx.h * HD, qrow);
+              break;
+            }
+          }
         }
         ++wi;
       }
