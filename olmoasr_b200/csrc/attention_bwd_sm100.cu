@@ -637,7 +637,12 @@ extern "C" int oasr_attention_bwd(const void* q, int64_t ldq, const void* k, int
   const int64_t n_work = ceil_div(Tkv, BKV) * H * B;
   OASR_REQUIRE(n_work < (int64_t(1) << 31), "attention_bwd: too many work items");
   static const bool persistent = [] { const char* e = getenv("OASR_BWD_PERSISTENT"); return !(e && e[0] == '0'); }();
-  const unsigned grid = persistent ? (unsigned)(n_work < num_sms() ? n_work : num_sms()) : (unsigned)n_work;
+  int64_t ctas = num_sms();
+  if (const char* cap = getenv("OASR_ATTN_MAX_CTAS")) {   // tests: few CTAs, so that small problems walk the multi-item path
+    const long v = atol(cap);
+    if (v > 0 && v < ctas) ctas = v;
+  }
+  const unsigned grid = persistent ? (unsigned)(n_work < ctas ? n_work : ctas) : (unsigned)n_work;
   attention_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, st>>>(tmQ, tmK, tmV, tmdO, tmDQ, tmDK, tmDV, p, (int)n_work);
   OASR_LAUNCH_CHECK();
   const int64_t rows = B * Tq;

@@ -496,7 +496,12 @@ extern "C" int oasr_attention_fwd(const void* q, int64_t ldq, const void* k, int
   const int64_t n_work = ceil_div(Tq, 2 * BQ) * H * B;
   OASR_REQUIRE(n_work < (int64_t(1) << 31), "attention: too many work items");
   static const bool persistent = [] { const char* e = getenv("OASR_FWD_PERSISTENT"); return !(e && e[0] == '0'); }();
-  const unsigned grid = persistent ? (unsigned)(n_work < num_sms() ? n_work : num_sms()) : (unsigned)n_work;
+  int64_t ctas = num_sms();
+  if (const char* cap = getenv("OASR_ATTN_MAX_CTAS")) {   // tests: few CTAs, so that small problems walk the multi-item path
+    const long v = atol(cap);
+    if (v > 0 && v < ctas) ctas = v;
+  }
+  const unsigned grid = persistent ? (unsigned)(n_work < ctas ? n_work : ctas) : (unsigned)n_work;
   attention_fwd_kernel<<<grid, 384, ATT_SMEM, (cudaStream_t)stream>>>(tmQ, tmK, tmV, tmO, p, (int)n_work);
   OASR_LAUNCH_CHECK();
   return OASR_OK;

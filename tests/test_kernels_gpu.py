@@ -241,6 +241,20 @@ def test_attention_fwd_bwd(K, B, H, Tq, Tkv, causal, use_len):
     _close(dv, vr.grad, rtol=1.0 / 48)
 
 
+@pytest.mark.parametrize("ctas", [1, 5])
+@pytest.mark.parametrize("B,H,Tq,Tkv,causal,use_len", [
+    (3, 2, 448, 448, True, True),       # causal + lengths: items of 0 .. 4 query tiles, fully masked key tiles in between
+    (2, 2, 448, 1500, False, False),    # cross-attention: 48 backward items
+    (2, 3, 700, 700, False, True),      # ragged tiles + lengths
+])
+def test_attention_persistent_multi_item(K, monkeypatch, ctas, B, H, Tq, Tkv, causal, use_len):
+    """The attention kernels are persistent (one CTA walks over many work items).  At unit-test sizes there are fewer items
+    than SMs, so the grid is capped here: every CTA then crosses item boundaries (barrier parities carried across items, the
+    epilogue / next-item overlap, zero-work items) and the result must not depend on the number of CTAs."""
+    monkeypatch.setenv("OASR_ATTN_MAX_CTAS", str(ctas))
+    test_attention_fwd_bwd(K, B, H, Tq, Tkv, causal, use_len)
+
+
 # ------------------------------------------------------------------------------------------------ CE / embedding
 def test_cross_entropy_fwd_bwd(K):
     torch.manual_seed(4)
