@@ -4,15 +4,15 @@
 // (encoder self, decoder causal+length self, cross).  Given Q, K, V, O, dO and the forward's log2-domain
 // LSE it produces dQ, dK, dV without ever materialising the (Tq x Tkv) score matrix in HBM.
 //
-// CTA = one 128-key tile of one (b, h); loops over the 128-query tiles that can see it:
+// Work item = one 128-key tile of one (b, h), looping over the 128-query tiles that can see it (a persistent CTA per SM
+// walks over the items, see the kernel's comment):
 //     S  = Q K^T            dP = dO V^T                      (tcgen05, accumulators in TMEM)
 //     P  = exp2(S c - LSE)  dS = P o (dP - D)                (thread r owns query row r: no reductions)
 //     dV += P^T dO          dK += dS^T Q        dQ_i = dS K  (P / dS go through swizzled smem as bf16;
 //                                                             the "transposes" are MN-major descriptors)
 // dV and dK stay resident in TMEM for the whole loop and leave through swizzled smem tiles + one TMA store each; dQ_i is
-// drained per query tile into a swizzled fp32 smem tile
-// and reduced across key tiles with ONE bulk TMA reduce-add per 32-column half (cp.reduce.async.bulk.tensor .add)
-// into an fp32 scratch buffer (converted to bf16 afterwards).  (Per-thread red.global.add.v4 made the whole kernel
+// drained per query tile into a swizzled fp32 smem tile and reduced across key tiles with ONE bulk TMA reduce-add per
+// 32-column half (cp.reduce.async.bulk.tensor .add) into an fp32 scratch buffer (converted to bf16 afterwards).  (Per-thread red.global.add.v4 made the whole kernel
 // atomics-bound: ~6500 cycles per tile pair against ~1300 of tensor work.)
 // 8 compute warps (two per TMEM lane quarter, each taking half of the 128 key columns; packed FFMA2 / FADD2 /
 // FMUL2 math) + TMA warp + MMA warp + 4 dQ-drain warps; S / dP are released to the MMA warp as soon as they sit in
