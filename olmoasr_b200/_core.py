@@ -19,7 +19,6 @@ from typing import Dict, Iterable, Optional
 
 import numpy as np
 import torch
-import torch.nn.functional as F
 from torch import Tensor, nn
 
 from . import kernels as K

@@ -22,13 +22,12 @@ from __future__ import annotations
 
 import ctypes
 import math
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, Optional, Sequence, Tuple
 
 import torch
 from torch import Tensor
 
 from . import _lib
-from . import kernels as K
 from ._lib import DTYPE_BF16, DTYPE_F16, DTYPE_F32, DecAttnArgs, DecLinearArgs, DecSampleArgs, call, ptr, stream
 
 X_PLAIN, X_LAYERNORM, X_PARTIAL_SUM = 0, 1, 2

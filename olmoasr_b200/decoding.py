@@ -14,7 +14,7 @@ pass `tokenizer=` (an object with `.decode(list[int])`) to get text, otherwise `
 from __future__ import annotations
 
 from dataclasses import dataclass, field, replace
-from typing import TYPE_CHECKING, Iterable, List, Optional, Sequence, Tuple, Union
+from typing import TYPE_CHECKING, Iterable, List, Optional, Tuple, Union
 
 import numpy as np
 import torch

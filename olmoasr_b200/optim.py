@@ -15,7 +15,6 @@ step, as GradScaler + AdamW do); `state[p]["step"]` is refreshed from it when `s
 from __future__ import annotations
 
 import math
-from typing import Optional
 
 import numpy as np
 import torch

@@ -17,7 +17,7 @@ from typing import List, Optional, Tuple, Union
 import numpy as np
 import torch
 
-from .audio import FRAMES_PER_SECOND, HOP_LENGTH, N_FRAMES, N_SAMPLES, SAMPLE_RATE, log_mel_spectrogram, pad_or_trim
+from .audio import HOP_LENGTH, N_FRAMES, N_SAMPLES, SAMPLE_RATE, log_mel_spectrogram, pad_or_trim
 from .decoding import EOT, TIMESTAMP_BEGIN, DecodingOptions, DecodingResult, decode
 
 
