@@ -636,7 +636,8 @@ extern "C" int oasr_attention_bwd(const void* q, int64_t ldq, const void* k, int
   // one CTA per SM walking over (key tile, head, sample) items; OASR_BWD_PERSISTENT=0: one CTA per item (A/B)
   const int64_t n_work = ceil_div(Tkv, BKV) * H * B;
   OASR_REQUIRE(n_work < (int64_t(1) << 31), "attention_bwd: too many work items");
-  static const bool persistent = [] { const char* e = getenv("OASR_BWD_PERSISTENT"); return !(e && e[0] == '0'); }();
+  const char* pe = getenv("OASR_BWD_PERSISTENT");   // read on every call: the host layer flips it when collectives share the GPU
+  const bool persistent = !(pe && pe[0] == '0');
   int64_t ctas = num_sms();
   if (const char* cap = getenv("OASR_ATTN_MAX_CTAS")) {   // tests: few CTAs, so that small problems walk the multi-item path
     const long v = atol(cap);

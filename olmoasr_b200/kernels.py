@@ -5,6 +5,8 @@ kernel is launched; the kernels themselves never allocate.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -115,9 +117,30 @@ def attention_fwd(q, k, v, B, H, Tq, Tkv, causal=False, kv_len=None, scale=None,
     return out, lse
 
 
+_BWD_PERSISTENT_USER = os.environ.get("OASR_BWD_PERSISTENT")   # an explicit setting of the user always wins
+
+
+def _choose_attention_bwd_mode():
+    """The backward attention kernel is persistent (one CTA per SM walking over its share of the work items) unless NCCL
+    collectives run next to the backward pass.  A resident all-reduce kernel takes SMs away (its CTAs cannot share an SM with
+    a 224 KB CTA); a statically partitioned persistent grid then runs its displaced CTAs as a second wave -- the GEMMs, which
+    are persistent, stretch by 43 % on 8 GPUs where the one-CTA-per-item attention of the same run stretched by 14 %
+    (profiles/r02_step_profile_slabsync_8gpu.txt).  One CTA per item degrades in proportion to the SMs it loses, so that
+    launch shape is used whenever the process is part of a multi-GPU job.  (Both shapes run the same code and are covered by
+    the parity tests; the forward pass does not overlap the gradient all-reduces and stays persistent.)"""
+    if _BWD_PERSISTENT_USER is not None:
+        return
+    d = torch.distributed
+    multi = d.is_available() and d.is_initialized() and d.get_world_size() > 1
+    want = "0" if multi else "1"
+    if os.environ.get("OASR_BWD_PERSISTENT") != want:
+        os.environ["OASR_BWD_PERSISTENT"] = want
+
+
 def attention_bwd(q, k, v, o, dout, lse, B, H, Tq, Tkv, causal=False, kv_len=None, scale=None, dq=None, dk=None, dv=None):
     for t, n in ((q, "q"), (k, "k"), (v, "v"), (o, "o"), (dout, "dout")):
         _bf16_2d(t, n)
+    _choose_attention_bwd_mode()
     if scale is None:
         scale = 64 ** -0.5
     dev = q.device
