@@ -120,19 +120,22 @@ def attention_fwd(q, k, v, B, H, Tq, Tkv, causal=False, kv_len=None, scale=None,
 _BWD_PERSISTENT_USER = os.environ.get("OASR_BWD_PERSISTENT")   # an explicit setting of the user always wins
 
 
-def _choose_attention_bwd_mode():
+def _choose_attention_bwd_mode(world_size=None):
     """The backward attention kernel is persistent (one CTA per SM walking over its share of the work items) unless NCCL
-    collectives run next to the backward pass.  A resident all-reduce kernel takes SMs away (its CTAs cannot share an SM with
-    a 224 KB CTA); a statically partitioned persistent grid then runs its displaced CTAs as a second wave -- the GEMMs, which
-    are persistent, stretch by 43 % on 8 GPUs where the one-CTA-per-item attention of the same run stretched by 14 %
+    collectives are resident next to the backward pass for a large part of it.  A resident all-reduce kernel takes SMs away
+    (its CTAs cannot share an SM with a 224 KB CTA); a statically partitioned persistent grid then runs its displaced CTAs as
+    a second wave -- on 8 GPUs the all-reduce kernels are resident for most of the backward and the (persistent) GEMMs
+    stretch by 43 % where the one-CTA-per-item attention of the same run stretched by 14 %
     (profiles/r02_step_profile_slabsync_8gpu.txt).  One CTA per item degrades in proportion to the SMs it loses, so that
-    launch shape is used whenever the process is part of a multi-GPU job.  (Both shapes run the same code and are covered by
-    the parity tests; the forward pass does not overlap the gradient all-reduces and stays persistent.)"""
+    launch shape is used in jobs of more than 2 GPUs; at 2 GPUs the collectives are resident for 9 ms of a 200 ms step and
+    the persistent shape measured faster (profiles/r02_bench_2gpu_final.json).  Both shapes run the same code and are
+    covered by the parity tests; the forward pass does not overlap the gradient all-reduces and stays persistent."""
     if _BWD_PERSISTENT_USER is not None:
         return
-    d = torch.distributed
-    multi = d.is_available() and d.is_initialized() and d.get_world_size() > 1
-    want = "0" if multi else "1"
+    if world_size is None:
+        d = torch.distributed
+        world_size = d.get_world_size() if (d.is_available() and d.is_initialized()) else 1
+    want = "0" if world_size > 2 else "1"
     if os.environ.get("OASR_BWD_PERSISTENT") != want:
         os.environ["OASR_BWD_PERSISTENT"] = want
 

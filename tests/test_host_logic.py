@@ -194,12 +194,15 @@ def _ddp_worker(rank, world, port, out):
     dist.all_gather(gathered, g)
     t = torch.tensor([float(rank + 1) * 10.0])
     dist.all_reduce(t, op=dist.ReduceOp.MAX)   # bench.py: max-over-ranks step time
-    # inside a multi-rank job the backward attention kernel is launched one CTA per work item (kernels.py explains why)
+    # the backward attention kernel's launch shape follows the size of the job (kernels.py explains why): persistent up to
+    # 2 ranks, one CTA per work item beyond
     from olmoasr_b200 import kernels as K
     os.environ.pop("OASR_BWD_PERSISTENT", None)
     K._BWD_PERSISTENT_USER = None
     K._choose_attention_bwd_mode()
     bwd_mode = os.environ.get("OASR_BWD_PERSISTENT")
+    K._choose_attention_bwd_mode(world_size=8)
+    bwd_mode += os.environ.get("OASR_BWD_PERSISTENT")
     if rank == 0:
         torch.save({"grads": gathered, "lens": lens, "tmax": float(t), "bwd_mode": bwd_mode}, out)
     dist.barrier()
@@ -213,7 +216,7 @@ def test_data_parallel_semantics_world2_gloo(tmp_path):
     r = torch.load(out, weights_only=False)
     assert torch.allclose(r["grads"][0], r["grads"][1])           # gradients are averaged across ranks
     assert r["tmax"] == 20.0
-    assert r["bwd_mode"] == "0"
+    assert r["bwd_mode"] == "10"      # 2 ranks: persistent; 8 ranks: one CTA per item
     from olmoasr_b200 import kernels as K          # ... and persistent in a single-process job, unless the user said otherwise
     saved, user = os.environ.pop("OASR_BWD_PERSISTENT", None), K._BWD_PERSISTENT_USER
     try:
