@@ -124,9 +124,10 @@ def _choose_attention_bwd_mode(world_size=None):
     """The backward attention kernel is persistent (one CTA per SM walking over its share of the work items) unless NCCL
     collectives are resident next to the backward pass for a large part of it.  A resident all-reduce kernel takes SMs away
     (its CTAs cannot share an SM with a 224 KB CTA); a statically partitioned persistent grid then runs its displaced CTAs as
-    a second wave -- on 8 GPUs the all-reduce kernels are resident for most of the backward and the (persistent) GEMMs
-    stretch by 43 % where the one-CTA-per-item attention of the same run stretched by 14 %
-    (profiles/r02_step_profile_slabsync_8gpu.txt).  One CTA per item degrades in proportion to the SMs it loses, so that
+    a second wave -- between the 1-GPU and the 8-GPU profile (side stream on in both) the persistent GEMMs' kernel time grows
+    from 120 to 147 ms (+22 %) where the then one-CTA-per-item attention backward grew from 50.5 to 55.1 ms (+9 %)
+    (profiles/r02_step_profile_sidestream.txt, r02_step_profile_slabsync_8gpu.txt).  One CTA per item degrades in proportion to
+    the SMs it loses (32 of 148: +28 % while a collective is resident, against +100 % for a displaced second wave), so that
     launch shape is used in jobs of more than 2 GPUs; at 2 GPUs the collectives are resident for 9 ms of a 200 ms step and
     the persistent shape measured faster (profiles/r02_bench_2gpu_final.json).  Both shapes run the same code and are
     covered by the parity tests; the forward pass does not overlap the gradient all-reduces and stays persistent."""
